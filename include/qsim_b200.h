@@ -1,0 +1,160 @@
+/*
+ * qsim_b200.h -- C ABI of libqsim_b200.so, the B200-native (sm_100a) state-vector
+ * engine that replaces qsim's CUDA Simulator / StateSpace / VectorSpace
+ * backends (reference: quantumlib/qsim @ 502b4a37, paths relative to its root).
+ *
+ * Plain pointers and sizes only.  Every entry point names the reference
+ * interface it replaces.  The header-only C++ mirror of qsim's duck-typed
+ * backend API (include/qsim_b200/simulator_b200.h, statespace_b200.h,
+ * vectorspace_b200.h) and the Python mirror (qsim_b200/) are both thin shims
+ * over this file.
+ *
+ * STATE LAYOUT.  A state of n qubits is a device array of 2*2^n scalars
+ * (float or double) in qsim's *normal order*: amplitude i = (s[2i], s[2i+1]),
+ * qubit q <-> bit q of i (lib/simulator.h:40-66).  This is the layout
+ * StateSpaceBasic uses on the CPU (lib/statespace_basic.h:84-105) and the one
+ * qsim's pybind layer hands to Python, so InternalToNormalOrder /
+ * NormalToInternalOrder (lib/statespace_cuda.h:85-107) are no-ops here.
+ *
+ * GATE MATRICES are caller-owned HOST pointers, row-major 2^G x 2^G,
+ * interleaved (re,im), same scalar type as the state, bit k of the row/column
+ * index <-> qs[k] (lib/matrix.h:26-33); they are consumed before the call
+ * returns.  qs must be sorted ascending like the reference requires
+ * (lib/simulator_cuda.h:72).
+ *
+ * ERRORS.  Every function returns a qb200_status.  Nothing prints or exits:
+ * the C++ shim maps QB200_ERR_CUDA to the reference's "print + exit"
+ * convention (lib/util_cuda.h:31-39) and QB200_ERR_OOM to Null()
+ * (lib/vectorspace_cuda.h:90-95).
+ *
+ * STREAMS.  All work of a context is enqueued on that context's stream
+ * (default: the legacy default stream, like the reference).  Gate application
+ * and state initialisation are asynchronous; calls that return a value to the
+ * host synchronise the stream.
+ */
+#ifndef QSIM_B200_H_
+#define QSIM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  QB200_OK = 0,
+  QB200_ERR_CUDA = 1,        /* a CUDA runtime call failed; see qb200_last_cuda_error */
+  QB200_ERR_OOM = 2,         /* device allocation failed */
+  QB200_ERR_INVALID = 3,     /* bad argument (qubit out of range, mismatch ...) */
+  QB200_ERR_UNSUPPORTED = 4  /* gate size outside the reference's limits; state untouched */
+} qb200_status;
+
+typedef enum { QB200_F32 = 0, QB200_F64 = 1 } qb200_dtype;
+
+typedef struct qb200_ctx qb200_ctx;
+
+/* ---- library / context ------------------------------------------------- */
+/* ABI version of this header (bumped on any signature change). */
+int qb200_abi_version(void);
+int qb200_device_count(int* count);
+/* Per-object resources: stream handle, reduction scratch, pinned result slot.
+ * Replaces the members SimulatorCUDA / StateSpaceCUDA own
+ * (lib/simulator_cuda.h:52-62,899-915; lib/statespace_cuda.h:378-390).
+ * device < 0 means "the current device".  Cheap: allocations are lazy. */
+int qb200_ctx_create(int device, qb200_ctx** ctx);
+int qb200_ctx_destroy(qb200_ctx* ctx);
+/* stream is a cudaStream_t; NULL selects the legacy default stream. */
+int qb200_ctx_set_stream(qb200_ctx* ctx, void* stream);
+/* cudaError_t of the last failed runtime call on this context, and its text. */
+int qb200_last_cuda_error(const qb200_ctx* ctx);
+const char* qb200_last_cuda_error_string(const qb200_ctx* ctx);
+/* Number of kernels this context has launched (bench.py's gpu_launches). */
+uint64_t qb200_launch_count(const qb200_ctx* ctx);
+/* Kernel-selection overrides for experiments: key/value pairs, see DESIGN.md. */
+int qb200_ctx_set_tuning(qb200_ctx* ctx, const char* key, int value);
+/* Event timing on the context's stream (CUDA events). */
+int qb200_timer_start(qb200_ctx* ctx);
+int qb200_timer_stop_ms(qb200_ctx* ctx, float* ms);
+
+/* ---- VectorSpace (lib/vectorspace_cuda.h:43-167) ------------------------ */
+/* StateSpaceCUDA::MinSize (lib/statespace_cuda.h:81-83): scalars per state. */
+uint64_t qb200_min_size(unsigned num_qubits);
+/* VectorSpaceCUDA::Create(n) (:87-96).  QB200_ERR_OOM on failure. */
+int qb200_state_alloc(unsigned num_qubits, int dtype, void** state);
+/* detail::free (:31-33) */
+int qb200_state_free(void* state);
+/* Copy state->state / state->host / host->state (:112-160).  `count` is in
+ * scalars; host buffers may be pageable.  Blocking, like the reference. */
+int qb200_copy_d2d(qb200_ctx* ctx, int dtype, const void* src, void* dst, uint64_t count);
+int qb200_copy_d2h(qb200_ctx* ctx, int dtype, const void* src, void* host_dst, uint64_t count);
+int qb200_copy_h2d(qb200_ctx* ctx, int dtype, const void* host_src, void* dst, uint64_t count);
+/* VectorSpaceCUDA::DeviceSync (:162-164): waits for the context's stream. */
+int qb200_sync(qb200_ctx* ctx);
+
+/* ---- Simulator (lib/simulator_cuda.h) ---------------------------------- */
+/* SimulatorCUDA::ApplyGate (:70-125): in place, num_targets in [0,6].
+ * More than 6 targets -> QB200_ERR_UNSUPPORTED (the reference ignores them). */
+int qb200_apply_gate(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits,
+                     const unsigned* qs, unsigned num_targets, const void* matrix);
+/* SimulatorCUDA::ApplyControlledGate (:135-207): bit i of cvals is the required
+ * value of the i-th lowest control qubit (lib/simulator.h:364-375).
+ * num_targets in [0,4] like the reference (:162-164); num_controls == 0
+ * forwards to qb200_apply_gate. */
+int qb200_apply_controlled_gate(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits,
+                                const unsigned* qs, unsigned num_targets,
+                                const unsigned* cqs, unsigned num_controls, uint64_t cvals,
+                                const void* matrix);
+/* SimulatorCUDA::ExpectationValue (:216-260): <psi|M|psi>, num_targets in [1,6],
+ * products in the state's precision, accumulation in double.  Synchronises. */
+int qb200_expectation_value(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits,
+                            const unsigned* qs, unsigned num_targets, const void* matrix,
+                            double out_re_im[2]);
+
+/* ---- StateSpace (lib/statespace_cuda.h, lib/statespace.h) -------------- */
+int qb200_set_all_zeros(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits);      /* :109-112 */
+int qb200_set_state_zero(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits);     /* :130-135 */
+int qb200_set_state_uniform(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits);  /* :115-127 */
+int qb200_get_ampl(qb200_ctx* ctx, int dtype, const void* state, uint64_t i, double out_re_im[2]); /* :138-145 */
+int qb200_set_ampl(qb200_ctx* ctx, int dtype, void* state, uint64_t i, double re, double im);      /* :148-164 */
+/* BulkSetAmpl (:166-187): state[i] = (re,im) where ((i & mask) == bits) ^ exclude. */
+int qb200_bulk_set_ampl(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits,
+                        uint64_t mask, uint64_t bits, double re, double im, int exclude);
+int qb200_add(qb200_ctx* ctx, int dtype, const void* src, void* dest, unsigned num_qubits); /* :189-204 */
+int qb200_multiply(qb200_ctx* ctx, int dtype, double a, void* state, unsigned num_qubits);  /* :206-217 */
+/* InnerProduct = sum conj(s1) s2 (:219-229, lib/util_cuda.h:108-114), RealInnerProduct
+ * (:231-237), Norm (:239-241).  Double accumulation, run-to-run deterministic. */
+int qb200_inner_product(qb200_ctx* ctx, int dtype, const void* s1, const void* s2,
+                        unsigned num_qubits, double out_re_im[2]);
+int qb200_real_inner_product(qb200_ctx* ctx, int dtype, const void* s1, const void* s2,
+                             unsigned num_qubits, double* out);
+int qb200_norm(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits, double* out);
+/* Sample (:243-312) minus the host RNG: sorted_rs are the sorted uniform
+ * [0,norm) values the caller drew (lib/util.h:67-85); out[m] = first index k
+ * whose cumulative probability exceeds sorted_rs[m]; 2^n - 1 when none does
+ * (lib/statespace_basic.h:227-229). */
+int qb200_sample(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits,
+                 const double* sorted_rs, uint64_t num_samples, uint64_t* out);
+/* Host helper = GenerateRandomValues<double> (lib/util.h:67-85): std::mt19937(seed),
+ * uniform_real_distribution(0,max_value), sorted ascending. */
+int qb200_generate_random_values(uint64_t num_samples, unsigned seed, double max_value, double* out);
+/* PartialNorms (:331-355): the state is cut into qb200_partial_norms_count(n)
+ * equal contiguous chunks; out[m] = sum |amp|^2 over chunk m. */
+uint64_t qb200_partial_norms_count(unsigned num_qubits);
+int qb200_partial_norms(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits, double* out);
+/* FindMeasuredBits (:357-373): inside chunk m, first index whose running sum
+ * exceeds r; returns index & mask. */
+int qb200_find_measured_bits(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits,
+                             uint64_t m, double r, uint64_t mask, uint64_t* out_bits);
+/* Collapse (:316-329): zero amplitudes with (i & mask) != bits, renormalise
+ * the rest by 1/sqrt(masked norm).  out_norm (may be NULL) receives that norm. */
+int qb200_collapse(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits,
+                   uint64_t mask, uint64_t bits, double* out_norm);
+/* InternalToNormalOrder / NormalToInternalOrder (:85-107): identity here. */
+int qb200_internal_to_normal_order(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits);
+int qb200_normal_to_internal_order(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif  /* QSIM_B200_H_ */

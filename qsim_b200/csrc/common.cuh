@@ -1,0 +1,116 @@
+// common.cuh -- shared plumbing for libqsim_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/qsim_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libqsim_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace qb200 {
+
+constexpr int kNumSMs = 148;           // B200
+constexpr unsigned kMaxTargets = 6;    // lib/simulator_cuda.h:96-98
+constexpr unsigned kMaxCtrlTargets = 4;  // lib/simulator_cuda.h:162-164
+constexpr unsigned kMaxQubits = 40;
+// Chunk of the state one partial norm covers (PartialNorms / Sample /
+// FindMeasuredBits share it): 2^13 amplitudes, the same granularity as the
+// reference's default 512 threads x 16 dblocks (lib/statespace_cuda.h:59-70).
+constexpr unsigned kChunkBits = 13;
+
+template <typename FP> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+struct Tuning {
+  int gate_mode = -1;      // -1 auto; 0 = one amplitude per thread; 1 = two (128-bit)
+  int block = 0;           // threads per block override for gate kernels (0 = auto)
+  int force_generic = 0;   // 1 = always use the runtime-generic gate kernel
+  int tile = -1;           // -1 auto; 0 = never use the smem-tile kernel; 1 = always when legal
+};
+
+}  // namespace qb200
+
+struct qb200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  void* scratch = nullptr;        // device scratch (reduction partials, chunk sums, samples)
+  size_t scratch_bytes = 0;
+  void* pinned = nullptr;         // pinned host result slot
+  size_t pinned_bytes = 0;
+  void* d_mat = nullptr;          // device copy of matrices too big for kernel parameters
+  int last_error = 0;             // cudaError_t
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  qb200::Tuning tune;
+};
+
+namespace qb200 {
+
+// Records a failed runtime call in the context and turns it into a status.
+inline int cuda_status(qb200_ctx* ctx, cudaError_t e) {
+  if (e == cudaSuccess) return QB200_OK;
+  if (ctx) ctx->last_error = (int) e;
+  (void) cudaGetLastError();  // clear the sticky flag of non-fatal errors
+  return e == cudaErrorMemoryAllocation ? QB200_ERR_OOM : QB200_ERR_CUDA;
+}
+
+#define QB_CUDA(ctx, call)                                   \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return ::qb200::cuda_status((ctx), e__); \
+  } while (0)
+
+#define QB_LAUNCHED(ctx)                                      \
+  do {                                                        \
+    ++(ctx)->launches;                                        \
+    cudaError_t e__ = cudaPeekAtLastError();                  \
+    if (e__ != cudaSuccess) return ::qb200::cuda_status((ctx), e__); \
+  } while (0)
+
+// Lazily grown device scratch / pinned host slot.
+int ensure_scratch(qb200_ctx* ctx, size_t bytes);
+int ensure_pinned(qb200_ctx* ctx, size_t bytes);
+int ensure_dmat(qb200_ctx* ctx);
+
+struct DeviceGuard {
+  explicit DeviceGuard(const qb200_ctx* ctx) {
+    cudaGetDevice(&prev_);
+    if (prev_ != ctx->device) { cudaSetDevice(ctx->device); switched_ = true; }
+  }
+  ~DeviceGuard() { if (switched_) cudaSetDevice(prev_); }
+  int prev_ = 0;
+  bool switched_ = false;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of up to two doubles; result valid in thread 0.  Fixed
+// summation tree -> run-to-run deterministic.
+template <int NT>
+__device__ __forceinline__ void block_sum2(double& a, double& b) {
+  __shared__ double sa[NT / 32], sb[NT / 32];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sa[w] = a; sb[w] = b; }
+  __syncthreads();
+  if (w == 0) {
+    a = lane < NT / 32 ? sa[lane] : 0.0;
+    b = lane < NT / 32 ? sb[lane] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+  __syncthreads();
+}
+
+}  // namespace qb200

@@ -1,0 +1,56 @@
+// gates_api.cu -- Simulator entry points of the C ABI (lib/simulator_cuda.h:70-260).
+#include "common.cuh"
+
+namespace qb200 {
+#define QB_DECL(name, FP)                                                                   \
+  int name(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned nq,             \
+           const unsigned* cqs, unsigned nc, uint64_t cvals, const FP* m, double* out);
+QB_DECL(gate_apply_f32, float)
+QB_DECL(gate_apply_f64, double)
+QB_DECL(gate_expect_f32, float)
+QB_DECL(gate_expect_f64, double)
+#undef QB_DECL
+}  // namespace qb200
+
+using namespace qb200;
+
+extern "C" {
+
+int qb200_apply_controlled_gate(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits,
+                                const unsigned* qs, unsigned num_targets, const unsigned* cqs,
+                                unsigned num_controls, uint64_t cvals, const void* matrix) {
+  // lib/simulator_cuda.h:96-98 (more than 6 targets) and :162-164 (more than 4
+  // targets under control) are "not implemented" in the reference: state untouched.
+  if (num_targets > kMaxTargets) return QB200_ERR_UNSUPPORTED;
+  if (num_controls > 0 && num_targets > kMaxCtrlTargets) return QB200_ERR_UNSUPPORTED;
+  if (dtype == QB200_F32)
+    return gate_apply_f32(ctx, (float*) state, num_qubits, qs, num_targets, cqs, num_controls,
+                          cvals, (const float*) matrix, nullptr);
+  if (dtype == QB200_F64)
+    return gate_apply_f64(ctx, (double*) state, num_qubits, qs, num_targets, cqs, num_controls,
+                          cvals, (const double*) matrix, nullptr);
+  return QB200_ERR_INVALID;
+}
+
+int qb200_apply_gate(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits,
+                     const unsigned* qs, unsigned num_targets, const void* matrix) {
+  return qb200_apply_controlled_gate(ctx, dtype, state, num_qubits, qs, num_targets, nullptr, 0, 0,
+                                     matrix);
+}
+
+int qb200_expectation_value(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits,
+                            const unsigned* qs, unsigned num_targets, const void* matrix,
+                            double out_re_im[2]) {
+  if (!out_re_im) return QB200_ERR_INVALID;
+  out_re_im[0] = out_re_im[1] = 0;  // the reference returns 0 for unsupported sizes (:259)
+  if (num_targets > kMaxTargets) return QB200_ERR_UNSUPPORTED;
+  if (dtype == QB200_F32)
+    return gate_expect_f32(ctx, (float*) state, num_qubits, qs, num_targets, nullptr, 0, 0,
+                           (const float*) matrix, out_re_im);
+  if (dtype == QB200_F64)
+    return gate_expect_f64(ctx, (double*) state, num_qubits, qs, num_targets, nullptr, 0, 0,
+                           (const double*) matrix, out_re_im);
+  return QB200_ERR_INVALID;
+}
+
+}  // extern "C"

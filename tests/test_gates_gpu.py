@@ -1,0 +1,178 @@
+"""Parity of the CUDA gate path (through the C ABI) against the CPU oracle.
+
+Mirrors the reference's own simulator tests (tests/simulator_testfixture.h):
+TestMultiQubitGates (:1147-1212), TestControlledGates (:1215-1362),
+TestGlobalPhaseGate (:1365-1413), TestExpectationValue1 (:1416-1472).
+Tolerances: fp32 per-amplitude |d| <= 1e-5 (north_star), in practice ~1e-7;
+fp64 <= 1e-12.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+from conftest import random_matrix, random_state, random_unitary
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.complex64: 2e-6, np.complex128: 1e-13}
+RDT = {np.complex64: np.float32, np.complex128: np.float64}
+
+
+def backends(cdt):
+    import qsim_b200
+    return qsim_b200.StateSpaceB200(RDT[cdt]), qsim_b200.SimulatorB200(RDT[cdt])
+
+
+def target_sets(n, g):
+    """lowest, highest, scattered and mixed target layouts."""
+    if g == 0:
+        return [[]]
+    sets = {tuple(range(g)), tuple(range(n - g, n))}
+    if n >= 2 * g:
+        sets.add(tuple(range(0, 2 * g, 2)))
+        sets.add(tuple(range(1, 2 * g, 2)))
+    if n >= 6 + g:
+        sets.add(tuple(range(5, 5 + g)))
+        sets.add(tuple([0] + list(range(6, 4 + g)) + [n - 1]) if g >= 2 else (n - 1,))
+    rng = np.random.default_rng(100 * n + g)
+    for _ in range(2):
+        sets.add(tuple(sorted(rng.choice(n, size=g, replace=False).tolist())))
+    return [list(s) for s in sets if len(s) == g]
+
+
+@pytest.mark.parametrize("cdt", [np.complex64, np.complex128])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 6, 9, 13, 16])
+def test_apply_gate_matches_oracle(oracle, cdt, n):
+    ss, sim = backends(cdt)
+    for g in range(0, min(n, 6) + 1):
+        for k, qs in enumerate(target_sets(n, g)):
+            host = random_state(n, cdt, seed=n * 1000 + g * 10 + k)
+            m = random_unitary(g, seed=g * 7 + k, cdtype=cdt)
+            st = ss.Create(n)
+            ss.from_numpy(host, st)
+            sim.ApplyGate(qs, m, st)
+            got = ss.to_numpy(st)
+            want = oracle.apply_gate(host.copy(), qs, m)
+            err = np.abs(got - want).max()
+            assert err <= TOL[cdt], (n, qs, err)
+
+
+@pytest.mark.parametrize("cdt", [np.complex64, np.complex128])
+def test_kernel_variants_agree(oracle, cdt):
+    """register kernels (1 and 2 amplitudes per thread) and the runtime-generic
+    kernel must all reproduce the oracle."""
+    n = 14
+    for variant in ({"gate_mode": 0}, {"force_generic": 1}, {"tile": 0}, {"tile": 1}):
+        ss, sim = backends(cdt)
+        for key, val in variant.items():
+            sim.set_tuning(key, val)
+        for g in range(0, 7):
+            for k, qs in enumerate(target_sets(n, g)):
+                host = random_state(n, cdt, seed=g * 10 + k)
+                m = random_matrix(g, seed=g * 7 + k, cdtype=cdt)
+                st = ss.Create(n)
+                ss.from_numpy(host, st)
+                sim.ApplyGate(qs, m, st)
+                err = np.abs(ss.to_numpy(st) - oracle.apply_gate(host.copy(), qs, m)).max()
+                assert err <= TOL[cdt], (variant, qs, err)
+
+
+@pytest.mark.parametrize("cdt", [np.complex64, np.complex128])
+@pytest.mark.parametrize("n", [3, 6, 8, 11])
+def test_controlled_gates_match_oracle(oracle, cdt, n):
+    """exhaustive-ish control/target masks, cvals all-0 / all-1 / mixed, non-unitary
+    matrix (tests/simulator_testfixture.h:1215-1362)."""
+    ss, sim = backends(cdt)
+    rng = np.random.default_rng(n)
+    cases = []
+    for g in range(0, min(4, n - 1) + 1):
+        for c in range(1, min(3, n - g) + 1):
+            for _ in range(4):
+                perm = rng.permutation(n)[: g + c].tolist()
+                qs, cqs = sorted(perm[:g]), sorted(perm[g:])
+                for cvals in {0, (1 << c) - 1, int(rng.integers(0, 1 << c))}:
+                    cases.append((qs, cqs, cvals))
+    # low controls and low targets explicitly
+    if n >= 6:
+        cases += [([1, 3], [0, 2], 0b10), ([0], [1, 2, 3], 0b111), ([5], [0], 1), ([0, 1, 2, 3], [4], 0),
+                  ([], [0], 1), ([], [2, 5], 0b01)]
+    for k, (qs, cqs, cvals) in enumerate(cases):
+        host = random_state(n, cdt, seed=k)
+        m = random_matrix(len(qs), seed=k, cdtype=cdt)
+        st = ss.Create(n)
+        ss.from_numpy(host, st)
+        sim.ApplyControlledGate(qs, cqs, cvals, m, st)
+        got = ss.to_numpy(st)
+        want = oracle.apply_controlled_gate(host.copy(), qs, cqs, cvals, m)
+        err = np.abs(got - want).max()
+        assert err <= TOL[cdt], (qs, cqs, cvals, err)
+
+
+@pytest.mark.parametrize("cdt", [np.complex64, np.complex128])
+@pytest.mark.parametrize("n", [1, 4, 7, 12, 16])
+def test_expectation_value_matches_oracle(oracle, cdt, n):
+    ss, sim = backends(cdt)
+    for g in range(1, min(n, 6) + 1):
+        for k, qs in enumerate(target_sets(n, g)):
+            host = random_state(n, cdt, seed=g * 10 + k)
+            m = random_matrix(g, seed=g + k, cdtype=cdt)
+            st = ss.Create(n)
+            ss.from_numpy(host, st)
+            got = sim.ExpectationValue(qs, m, st)
+            want = oracle.expectation_value(host, qs, m)
+            tol = 1e-6 if cdt == np.complex64 else 1e-13
+            assert abs(got - want) <= tol, (n, qs, got, want)
+            # read-only: state unchanged, bit for bit
+            assert np.array_equal(ss.to_numpy(st), host)
+
+
+def test_gate_application_is_deterministic():
+    """EXPECT_EQ bit-identical amplitudes across repeated runs
+    (tests/simulator_testfixture.h:735-764)."""
+    import qsim_b200
+    ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
+    n = 18
+    host = random_state(n, np.complex64, 3)
+    outs = []
+    for _ in range(3):
+        st = ss.Create(n)
+        ss.from_numpy(host, st)
+        for k, qs in enumerate([[0, 1, 2, 3], [4, 9, 13, 17], [2, 6], [1, 5, 7, 11, 16]]):
+            sim.ApplyGate(qs, random_unitary(len(qs), k, np.complex64), st)
+        sim.ApplyControlledGate([3, 8], [0, 12], 0b11, random_unitary(2, 9, np.complex64), st)
+        outs.append(ss.to_numpy(st))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_unsupported_sizes_are_ignored():
+    """>6 targets, or >4 targets under control: state untouched (lib/simulator_cuda.h:96-98,162-164)."""
+    import qsim_b200
+    ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
+    n = 9
+    host = random_state(n, np.complex64, 5)
+    st = ss.Create(n)
+    ss.from_numpy(host, st)
+    sim.ApplyGate(list(range(7)), np.zeros(2 << 14, np.float32), st)
+    sim.ApplyControlledGate([0, 1, 2, 3, 4], [8], 1, np.zeros(2 << 10, np.float32), st)
+    assert np.array_equal(ss.to_numpy(st), host)
+
+
+def test_unitarity_round_trip_large():
+    """size-independent property at a BASELINE-like size: U then U^dagger restores the state."""
+    import qsim_b200
+    ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
+    n = 26
+    st = ss.Create(n)
+    ss.SetStateUniform(st)
+    layouts = [[0, 1, 2, 3], [3, 9, 17, 25], [22, 23, 24, 25], [5, 6], [0, 25], [1, 8, 13, 19, 24], [2, 4, 6, 10, 20, 21]]
+    us = [random_unitary(len(q), i, np.complex64) for i, q in enumerate(layouts)]
+    for q, u in zip(layouts, us):
+        sim.ApplyGate(q, u, st)
+    assert abs(ss.Norm(st) - 1.0) < 1e-5
+    for q, u in reversed(list(zip(layouts, us))):
+        sim.ApplyGate(q, np.ascontiguousarray(u.conj().T), st)
+    amp = 2.0 ** (-n / 2)
+    got = ss.to_numpy(st)
+    assert np.abs(got - amp).max() < 1e-5 * amp * 100
+    assert abs(ss.Norm(st) - 1.0) < 1e-5
