@@ -32,6 +32,7 @@ struct Tuning {
   int block = 0;           // threads per block override for gate kernels (0 = auto)
   int force_generic = 0;   // 1 = always use the runtime-generic gate kernel
   int tile = -1;           // -1 auto; 0 = never use the smem-tile kernel; 1 = always when legal
+  int prefetch = -1;       // -1 auto (on); 0 = no software-pipelined persistent loop
 };
 
 }  // namespace qb200

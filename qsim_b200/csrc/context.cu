@@ -201,6 +201,7 @@ int qb200_ctx_set_tuning(qb200_ctx* ctx, const char* key, int value) {
   else if (!std::strcmp(key, "block")) ctx->tune.block = value;
   else if (!std::strcmp(key, "force_generic")) ctx->tune.force_generic = value;
   else if (!std::strcmp(key, "tile")) ctx->tune.tile = value;
+  else if (!std::strcmp(key, "prefetch")) ctx->tune.prefetch = value;
   else return QB200_ERR_INVALID;
   return QB200_OK;
 }

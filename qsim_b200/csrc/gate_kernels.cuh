@@ -21,22 +21,69 @@ namespace qb200 {
 enum GateMode : int { kV1 = 0, kV2 = 1, kV2T = 2 };
 constexpr int kRowBatch = 4;  // rows of the unrolled mat-vec scheduled together
 
-// ---- matrix operand sources ------------------------------------------------
+// ---- matrix operand -----------------------------------------------------------
+// Passed by value as a __grid_constant__ kernel parameter: with rows and columns
+// unrolled every element is fetched by LDCU straight into uniform registers and
+// used as a broadcast scalar operand -- no per-block matrix staging at all.
 template <typename FP, int G>
-struct MatParam {  // passed by value as a __grid_constant__ parameter
-  FP m[2 << (2 * G)];
-  __device__ __forceinline__ FP re(int r, int c) const { return m[2 * ((r << G) + c)]; }
-  __device__ __forceinline__ FP im(int r, int c) const { return m[2 * ((r << G) + c) + 1]; }
+struct MatParam {
+  FP m[2 << (2 * G)];  // row-major, interleaved (re, im), as the caller passes it
+  void fill(const FP* src) {
+    for (int i = 0; i < (2 << (2 * G)); ++i) m[i] = src[i];
+  }
 };
 
-template <typename FP, int G>
-struct MatGlobal {  // device pointer (matrices too big for the parameter space)
-  const FP* m;
-  __device__ __forceinline__ FP re(int r, int c) const { return __ldg(m + 2 * ((r << G) + c)); }
-  __device__ __forceinline__ FP im(int r, int c) const { return __ldg(m + 2 * ((r << G) + c) + 1); }
+// ---- complex values in registers ------------------------------------------------
+// fp32: one amplitude = one 64-bit register pair (re, im), exactly as an LDG.64 /
+// LDG.128 delivers it.  On sm_100 the scalar FFMA issues at half rate; the packed
+// FFMA2 (fma.rn.f32x2) does two FMAs per lane per issue.  One complex MAC
+//     acc += x * mr;   acc += (i x) * mi        with  i x = (-im, re)
+// is two FFMA2 whose first operand is the natural (or lane-swapped, ptxas folds
+// the swap/negate into operand modifiers) amplitude pair and whose second operand
+// is a broadcast uniform-register scalar: no packing moves, one LDCU.128 feeds
+// four FFMA2 per amplitude group.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+template <typename FP> struct CT;
+template <> struct CT<float> {
+  using type = uint64_t;
+  static __device__ __forceinline__ type make(float re, float im) { return pack2(re, im); }
+  static __device__ __forceinline__ void get(type v, float& re, float& im) { unpack2(v, re, im); }
+  static __device__ __forceinline__ type rot(type v) { float a, b; unpack2(v, a, b); return pack2(-b, a); }
+  static __device__ __forceinline__ type mac(type acc, type x, type ix, float mr, float mi) {
+    acc = fma2(x, pack2(mr, mr), acc);
+    return fma2(ix, pack2(mi, mi), acc);
+  }
+  static __device__ __forceinline__ void fence(type& v) { asm volatile("" : "+l"(v)); }
+};
+template <> struct CT<double> {
+  struct type { double re, im; };
+  static __device__ __forceinline__ type make(double re, double im) { return type{re, im}; }
+  static __device__ __forceinline__ void get(type v, double& re, double& im) { re = v.re; im = v.im; }
+  static __device__ __forceinline__ type rot(type v) { return v; }  // unused by mac
+  static __device__ __forceinline__ type mac(type acc, type x, type, double mr, double mi) {
+    acc.re = fma(x.re, mr, acc.re);
+    acc.re = fma(-x.im, mi, acc.re);
+    acc.im = fma(x.re, mi, acc.im);
+    acc.im = fma(x.im, mr, acc.im);
+    return acc;
+  }
+  static __device__ __forceinline__ void fence(type& v) { asm volatile("" : "+d"(v.re), "+d"(v.im)); }
 };
 
-// ---- 128-bit / 64-bit accessors -------------------------------------------
+// ---- 64-bit / 128-bit accessors -----------------------------------------------
 __device__ __forceinline__ void ld1(const float* p, float& a, float& b) {
   const float2 v = *reinterpret_cast<const float2*>(p); a = v.x; b = v.y;
 }
@@ -62,6 +109,22 @@ __device__ __forceinline__ void ld2(const double* p, double& a, double& b, doubl
 __device__ __forceinline__ void st2(double* p, double a, double b, double c, double d) {
   st1(p, a, b); st1(p + 2, c, d);
 }
+template <typename FP>
+__device__ __forceinline__ typename CT<FP>::type ldc1(const FP* p) {
+  FP a, b; ld1(p, a, b); return CT<FP>::make(a, b);
+}
+template <typename FP>
+__device__ __forceinline__ void ldc2(const FP* p, typename CT<FP>::type& u, typename CT<FP>::type& v) {
+  FP a, b, c, d; ld2(p, a, b, c, d); u = CT<FP>::make(a, b); v = CT<FP>::make(c, d);
+}
+template <typename FP>
+__device__ __forceinline__ void stc1(FP* p, typename CT<FP>::type u) {
+  FP a, b; CT<FP>::get(u, a, b); st1(p, a, b);
+}
+template <typename FP>
+__device__ __forceinline__ void stc2(FP* p, typename CT<FP>::type u, typename CT<FP>::type v) {
+  FP a, b, c, d; CT<FP>::get(u, a, b); CT<FP>::get(v, c, d); st2(p, a, b, c, d);
+}
 
 // Store addresses equal load addresses; left alone, the compiler keeps all 2^G
 // 64-bit addresses live across the whole mat-vec (32 registers at G=4).  This
@@ -71,60 +134,80 @@ __device__ __forceinline__ uint64_t late(uint64_t v) {
   return v;
 }
 
-// Scheduling fence between row batches of the unrolled mat-vec: the first
-// column operand of every later row "changes" here, so ptxas cannot start the
-// dependent FFMA chains of later rows early and blow up the register count.
-// Emits no instruction.
-__device__ __forceinline__ void row_fence(float& a, float& b) { asm volatile("" : "+f"(a), "+f"(b)); }
-__device__ __forceinline__ void row_fence(double& a, double& b) { asm volatile("" : "+d"(a), "+d"(b)); }
-
-// one output row of the complex mat-vec: (re,im) = sum_c M[r][c] * x[c]
-template <typename FP, int G, typename Mat>
-__device__ __forceinline__ void row_dot(const FP (&xr)[1 << G], const FP (&xi)[1 << G],
-                                        const Mat& mat, int r, FP& re, FP& im) {
+// one output row of the complex mat-vec: sum_c M[r][c] * x[c]
+template <typename FP, int G>
+__device__ __forceinline__ typename CT<FP>::type
+row_dot(const typename CT<FP>::type (&x)[1 << G], const typename CT<FP>::type (&ix)[1 << G],
+        const MatParam<FP, G>& mat, int r) {
   constexpr int N = 1 << G;
-  re = 0;
-  im = 0;
+  typename CT<FP>::type acc = CT<FP>::make(0, 0);
 #pragma unroll
   for (int c = 0; c < N; ++c) {
-    const FP mr = mat.re(r, c), mi = mat.im(r, c);
-    re = fma(xr[c], mr, re);
-    re = fma(-xi[c], mi, re);
-    im = fma(xr[c], mi, im);
-    im = fma(xi[c], mr, im);
+    const FP mr = mat.m[2 * ((r << G) + c)], mi = mat.m[2 * ((r << G) + c) + 1];
+    acc = CT<FP>::mac(acc, x[c], ix[c], mr, mi);
   }
+  return acc;
 }
 
 // ---------------------------------------------------------------------------
 // Register kernel.  FP, G, MODE compile-time; UNROLL = rows unrolled too.
 // EXPECT: read-only pass accumulating <x|M|x> into per-block partials.
+//   kV1  one group per thread, one amplitude per access (64-bit fp32 / 128-bit fp64)
+//   kV2  two groups per thread = the two amplitudes of one 128-bit access (bit 0 free)
+//   kV2T one group per thread, bit 0 is the lowest target: elements k, k+1 share a
+//        128-bit access
 // ---------------------------------------------------------------------------
-template <typename FP, int G, int MODE, bool UNROLL, bool EXPECT, int NT, int MINB, typename Mat>
+template <typename FP, int G, int MODE, bool UNROLL, bool EXPECT, bool PREFETCH, int NT, int MINB, typename Mat>
 __global__ void __launch_bounds__(NT, MINB)
 k_gate_reg(FP* __restrict__ st, const __grid_constant__ Geom g,
            const __grid_constant__ Mat mat, double* __restrict__ partials) {
   constexpr int N = 1 << G;
   constexpr int NV = MODE == kV2 ? 2 : 1;
+  using C = typename CT<FP>::type;
   double ere = 0, eim = 0;
 
-  for (uint64_t i = blockIdx.x * uint64_t{NT} + threadIdx.x; i < g.work;
-       i += uint64_t{gridDim.x} * NT) {
-    const uint64_t base = expand_index(i, g);
-    FP* const p = st + 2 * base;
-
-    FP xr[NV][N], xi[NV][N];
+  auto load_group = [&](uint64_t i, FP*& p, C (&x)[NV][N]) {
+    p = st + 2 * expand_index(i, g);
     if constexpr (MODE == kV1) {
 #pragma unroll
-      for (int k = 0; k < N; ++k) ld1(p + 2 * elem_offset<G>(k, g), xr[0][k], xi[0][k]);
+      for (int k = 0; k < N; ++k) x[0][k] = ldc1<FP>(p + 2 * elem_offset<G>(k, g));
     } else if constexpr (MODE == kV2) {
 #pragma unroll
-      for (int k = 0; k < N; ++k)
-        ld2(p + 2 * elem_offset<G>(k, g), xr[0][k], xi[0][k], xr[1][k], xi[1][k]);
-    } else {  // kV2T: target 0 is bit 0 -> elements k and k+1 are adjacent
+      for (int k = 0; k < N; ++k) ldc2<FP>(p + 2 * elem_offset<G>(k, g), x[0][k], x[1][k]);
+    } else {
 #pragma unroll
-      for (int k = 0; k < N; k += 2)
-        ld2(p + 2 * elem_offset<G>(k, g), xr[0][k], xi[0][k], xr[0][k + 1], xi[0][k + 1]);
+      for (int k = 0; k < N; k += 2) ldc2<FP>(p + 2 * elem_offset<G>(k, g), x[0][k], x[0][k + 1]);
     }
+  };
+
+  // PREFETCH: persistent grid-stride loop, the next group's loads are issued
+  // before the current group's mat-vec so every warp keeps a full group of
+  // HBM requests in flight while its FMA pipe is busy.
+  const uint64_t stride = uint64_t{gridDim.x} * NT;
+  uint64_t i = blockIdx.x * uint64_t{NT} + threadIdx.x;
+  FP* pn = st;
+  C xn[NV][N];
+  if constexpr (PREFETCH) {
+    if (i < g.work) load_group(i, pn, xn);
+  }
+
+  for (; i < g.work; i += stride) {
+    FP* p;
+    C x[NV][N], ix[NV][N];
+    if constexpr (PREFETCH) {
+      p = pn;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < N; ++k) x[v][k] = xn[v][k];
+      if (i + stride < g.work) load_group(i + stride, pn, xn);
+    } else {
+      load_group(i, p, x);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int k = 0; k < N; ++k) ix[v][k] = CT<FP>::rot(x[v][k]);
 
     if constexpr (EXPECT) {
       static_assert(UNROLL, "expectation kernels index x[r] at compile time");
@@ -132,24 +215,23 @@ k_gate_reg(FP* __restrict__ st, const __grid_constant__ Geom g,
       for (int v = 0; v < NV; ++v) {
 #pragma unroll
         for (int r = 0; r < N; ++r) {
-          if (r % kRowBatch == 0 && r > 0) row_fence(xr[v][0], xi[v][0]);
-          FP re, im;
-          row_dot<FP, G>(xr[v], xi[v], mat, r, re, im);
+          if (r % kRowBatch == 0 && r > 0) CT<FP>::fence(x[v][0]);
+          FP re, im, xr, xi;
+          CT<FP>::get(row_dot<FP, G>(x[v], ix[v], mat, r), re, im);
+          CT<FP>::get(x[v][r], xr, xi);
           // products in FP, accumulation in double (lib/simulator_basic.h:323-324)
-          ere += xr[v][r] * re + xi[v][r] * im;
-          eim += xr[v][r] * im - xi[v][r] * re;
+          ere += xr * re + xi * im;
+          eim += xr * im - xi * re;
         }
       }
     } else if constexpr (MODE == kV1) {
       auto body = [&](int r) {
-        FP re, im;
-        row_dot<FP, G>(xr[0], xi[0], mat, r, re, im);
-        st1(p + 2 * late(elem_offset<G>(r, g)), re, im);
+        stc1<FP>(p + 2 * late(elem_offset<G>(r, g)), row_dot<FP, G>(x[0], ix[0], mat, r));
       };
       if constexpr (UNROLL) {
 #pragma unroll
         for (int r = 0; r < N; ++r) {
-          if (r % kRowBatch == 0 && r > 0) row_fence(xr[0][0], xi[0][0]);
+          if (r % kRowBatch == 0 && r > 0) CT<FP>::fence(x[0][0]);
           body(r);
         }
       } else {
@@ -158,17 +240,16 @@ k_gate_reg(FP* __restrict__ st, const __grid_constant__ Geom g,
       }
     } else if constexpr (MODE == kV2) {
       auto body = [&](int r) {
-        FP re0, im0, re1, im1;
-        row_dot<FP, G>(xr[0], xi[0], mat, r, re0, im0);
-        row_dot<FP, G>(xr[1], xi[1], mat, r, re1, im1);
-        st2(p + 2 * late(elem_offset<G>(r, g)), re0, im0, re1, im1);
+        const C a = row_dot<FP, G>(x[0], ix[0], mat, r);
+        const C b = row_dot<FP, G>(x[1], ix[1], mat, r);
+        stc2<FP>(p + 2 * late(elem_offset<G>(r, g)), a, b);
       };
       if constexpr (UNROLL) {
 #pragma unroll
         for (int r = 0; r < N; ++r) {
           if (r % kRowBatch == 0 && r > 0) {
-            row_fence(xr[0][0], xi[0][0]);
-            row_fence(xr[1][0], xi[1][0]);
+            CT<FP>::fence(x[0][0]);
+            CT<FP>::fence(x[1][0]);
           }
           body(r);
         }
@@ -178,15 +259,14 @@ k_gate_reg(FP* __restrict__ st, const __grid_constant__ Geom g,
       }
     } else {
       auto body = [&](int r) {
-        FP re0, im0, re1, im1;
-        row_dot<FP, G>(xr[0], xi[0], mat, r, re0, im0);
-        row_dot<FP, G>(xr[0], xi[0], mat, r + 1, re1, im1);
-        st2(p + 2 * late(elem_offset<G>(r, g)), re0, im0, re1, im1);
+        const C a = row_dot<FP, G>(x[0], ix[0], mat, r);
+        const C b = row_dot<FP, G>(x[0], ix[0], mat, r + 1);
+        stc2<FP>(p + 2 * late(elem_offset<G>(r, g)), a, b);
       };
       if constexpr (UNROLL) {
 #pragma unroll
         for (int r = 0; r < N; r += 2) {
-          if (r % kRowBatch == 0 && r > 0) row_fence(xr[0][0], xi[0][0]);
+          if (r % kRowBatch == 0 && r > 0) CT<FP>::fence(x[0][0]);
           body(r);
         }
       } else {

@@ -4,7 +4,7 @@
 
 #include <cstring>
 
-#include "gate_kernels.cuh"
+#include "gate_pipe.cuh"
 
 namespace qb200 {
 
@@ -29,6 +29,38 @@ template <typename FP, int G> constexpr int min_blocks() {
 
 constexpr uint32_t kExpectMaxBlocks = kNumSMs * 8;
 
+// resident blocks per SM of a kernel (queried once per instantiation)
+template <typename K>
+int resident_blocks(K kern, int threads) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, 0) != cudaSuccess || nb < 1) {
+    (void) cudaGetLastError();
+    nb = 1;
+  }
+  return nb;
+}
+
+template <int G, int MODE, int PNT, int PD, int PMINB>
+int launch_pipe(qb200_ctx* ctx, float* st, const Geom& g, const MatParam<float, G>& mat) {
+  auto kern = k_gate_pipe<G, MODE, PNT, PD, PMINB>;
+  constexpr size_t smem = pipe_smem_bytes<G, MODE, PNT, PD>();
+  static const int occ = [&] {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PNT, smem) != cudaSuccess || nb < 1) {
+      (void) cudaGetLastError();
+      nb = 1;
+    }
+    return nb;
+  }();
+  const uint64_t need = (g.work + PNT - 1) / PNT;
+  const uint64_t persistent = uint64_t{kNumSMs} * occ;
+  const uint32_t blocks = (uint32_t) (need < persistent ? need : persistent);
+  kern<<<blocks, PNT, smem, ctx->stream>>>(st, g, mat);
+  QB_LAUNCHED(ctx);
+  return QB200_OK;
+}
+
 template <typename FP, int G, int MODE, bool EXPECT>
 int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) {
   constexpr int NT = block_threads<FP, G>();
@@ -36,7 +68,7 @@ int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) 
   constexpr bool UNROLL = G <= RegLimits<FP>::kMaxUnrollG;
   using Mat = MatParam<FP, G>;
   Mat mat;
-  std::memcpy(mat.m, m, sizeof(mat.m));
+  mat.fill(m);
   uint64_t blocks64 = (g.work + NT - 1) / NT;
   if (blocks64 > 0x7fffffffull) blocks64 = 0x7fffffffull;
   if constexpr (EXPECT) {
@@ -47,12 +79,36 @@ int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) 
       int rc = ensure_scratch(ctx, (2 * size_t{blocks} + 2) * sizeof(double));
       if (rc) return rc;
       double* partials = (double*) ctx->scratch;
-      k_gate_reg<FP, G, MODE, true, true, NT, MINB, Mat><<<blocks, NT, 0, ctx->stream>>>(st, g, mat, partials);
+      k_gate_reg<FP, G, MODE, true, true, false, NT, MINB, Mat><<<blocks, NT, 0, ctx->stream>>>(st, g, mat, partials);
       QB_LAUNCHED(ctx);
       return finish_expectation(ctx, partials, blocks, out);
     }
   } else {
-    k_gate_reg<FP, G, MODE, UNROLL, false, NT, MINB, Mat><<<(uint32_t) blocks64, NT, 0, ctx->stream>>>(st, g, mat, nullptr);
+    // fp32 G == 4: deep cp.async ring through shared memory (gate_pipe.cuh)
+    if constexpr (sizeof(FP) == 4 && G == 4) {
+      if (ctx->tune.tile != 0) {
+        switch (ctx->tune.block) {
+          case 1: return launch_pipe<G, MODE, 128, (MODE == kV2 ? 3 : 6), 2>(ctx, st, g, mat);
+          case 2: return launch_pipe<G, MODE, 256, (MODE == kV2 ? 2 : 4), 1>(ctx, st, g, mat);
+          case 3: return launch_pipe<G, MODE, 128, (MODE == kV2 ? 2 : 4), 3>(ctx, st, g, mat);
+          default: return launch_pipe<G, MODE, 256, (MODE == kV2 ? 2 : 3), 2>(ctx, st, g, mat);
+        }
+      }
+    }
+    // G >= 4 fp32 (single group per thread): software-pipelined persistent grid
+    constexpr bool kCanPrefetch = sizeof(FP) == 4 && G >= 4 && UNROLL && MODE != kV2;
+    if constexpr (kCanPrefetch) {
+      if (ctx->tune.prefetch != 0) {
+        auto kern = k_gate_reg<FP, G, MODE, UNROLL, false, true, NT, MINB, Mat>;
+        static const int occ = resident_blocks(kern, NT);
+        const uint64_t persistent = uint64_t{kNumSMs} * occ;
+        const uint32_t blocks = (uint32_t) (blocks64 < persistent ? blocks64 : persistent);
+        kern<<<blocks, NT, 0, ctx->stream>>>(st, g, mat, nullptr);
+        QB_LAUNCHED(ctx);
+        return QB200_OK;
+      }
+    }
+    k_gate_reg<FP, G, MODE, UNROLL, false, false, NT, MINB, Mat><<<(uint32_t) blocks64, NT, 0, ctx->stream>>>(st, g, mat, nullptr);
     QB_LAUNCHED(ctx);
     return QB200_OK;
   }
