@@ -90,6 +90,8 @@ int qb200_copy_d2h(qb200_ctx* ctx, int dtype, const void* src, void* host_dst, u
 int qb200_copy_h2d(qb200_ctx* ctx, int dtype, const void* host_src, void* dst, uint64_t count);
 /* VectorSpaceCUDA::DeviceSync (:162-164): waits for the context's stream. */
 int qb200_sync(qb200_ctx* ctx);
+/* The reference's static DeviceSync: cudaDeviceSynchronize on the current device. */
+int qb200_device_sync(void);
 
 /* ---- Simulator (lib/simulator_cuda.h) ---------------------------------- */
 /* SimulatorCUDA::ApplyGate (:70-125): in place, num_targets in [0,6].

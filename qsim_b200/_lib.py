@@ -37,6 +37,7 @@ SIGNATURES = {
     "qb200_copy_d2h": (_i, [_vp, _i, _vp, _vp, _u64]),
     "qb200_copy_h2d": (_i, [_vp, _i, _vp, _vp, _u64]),
     "qb200_sync": (_i, [_vp]),
+    "qb200_device_sync": (_i, []),
     "qb200_apply_gate": (_i, [_vp, _i, _vp, _u, _pu, _u, _vp]),
     "qb200_apply_controlled_gate": (_i, [_vp, _i, _vp, _u, _pu, _u, _pu, _u, _u64, _vp]),
     "qb200_expectation_value": (_i, [_vp, _i, _vp, _u, _pu, _u, _vp, _pd]),

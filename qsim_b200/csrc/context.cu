@@ -274,6 +274,14 @@ int qb200_copy_h2d(qb200_ctx* ctx, int dtype, const void* host_src, void* dst, u
   return QB200_OK;
 }
 
+int qb200_device_sync(void) {
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    (void) cudaGetLastError();
+    return QB200_ERR_CUDA;
+  }
+  return QB200_OK;
+}
+
 int qb200_sync(qb200_ctx* ctx) {
   if (!ctx) return QB200_ERR_INVALID;
   DeviceGuard guard(ctx);
