@@ -142,6 +142,106 @@ def run_reference_arm(args, rank):
     print(json.dumps(line))
 
 
+def run_sharded(args, rank, world, local_rank, dist):
+    """N > 1: weak scaling.  One 2^30-amplitude shard (8 GiB) per GPU, n = 30 + log2(N)
+    qubits, circuit built like circuit_q30 by tools/gen_rqc.py and fused by the reference
+    fuser (tests/golden/rqc_q<n>_d20_f4.trace).  Gates on global qubits trigger
+    local<->global swaps = grouped NCCL send/recv over NVLink (qsim_b200/sharded.py)."""
+    import torch
+    import qsim_b200
+    from qsim_b200.sharded import B200Engine, ShardedSimulator, plan_swaps
+
+    g = world.bit_length() - 1
+    n = 30 + g
+    trace = os.path.join(ROOT, "tests", "golden", f"rqc_q{n}_d20_f4.trace")
+    nq, ops = qsim_b200.read_trace(trace)
+    assert nq == n
+    eng = B200Engine(n - g, local_rank)
+    sim = ShardedSimulator(n, eng, dist=dist, rank=rank, world_size=world, transfer_scalars=1 << 28)
+    opq = [list(o.qubits) + list(o.controls) for o in ops]
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_run():
+        sim.pos = list(range(n))
+        sim.set_state_zero()
+        sim.run(ops, plan_swaps(opq, n, g))
+
+    for _ in range(max(args.warmup, 3)):
+        one_run()
+    barrier()
+    sim.reset_stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.sim.launch_count()
+    ev = []
+    for _ in range(args.steps):
+        sim.pos = list(range(n))
+        sim.set_state_zero()
+        torch.cuda.synchronize()
+        e0 = eng.event()
+        sim.run(ops, plan_swaps(opq, n, g))
+        ev.append((e0, eng.event()))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.sim.launch_count() - l0
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    exch_ms = sim.exchange_device_ms()
+    t = torch.tensor([dev_ms, exch_ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, exch_ms = float(t[0].item()), float(t[1].item())
+    ms_per_step = dev_ms / args.steps
+    total_bytes = len(ops) * 16.0 * (1 << n)
+    value = total_bytes / (ms_per_step * 1e-3) / 1e9
+    import copy
+    stats = copy.deepcopy(sim.stats)
+
+    e2e_ms = []
+    for it in range(1 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        one_run()
+        amps = [sim.get_ampl(i) for i in range(8)]
+        nrm = sim.norm()
+        torch.cuda.synchronize()
+        if it >= 1:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([float(np.mean(e2e_ms))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_step = float(t.item())
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        sent = stats.bytes_sent / args.steps
+        swaps = stats.swaps // args.steps
+        line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"rqc_q{n} depth 20 (tools/gen_rqc.py, circuit_q30 rules), max_fused_size 4: {len(ops)} fused-gate "
+                                       f"passes on a 2^{n}-amplitude fp32 state sharded over {world} GPUs (8 GiB shard each)",
+                           "l2": "shard (8 GiB) is 68x larger than L2",
+                           "multi_gpu": f"global-qubit sharding, {swaps} local<->global swaps per circuit "
+                                        f"(grouped NCCL send/recv), {stats.local_swap_passes // args.steps} local SWAP passes",
+                           "wall_time_s_per_circuit": ms_per_step * 1e-3},
+                "roofline": {"bound": "hbm", "achieved": value / world, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
+                             "frac": value / world / float(peaks["hbm_gbs"]), "traffic": None,
+                             "note": "per-GPU algorithmic gate bytes over the whole step (swap time included)",
+                             "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})"},
+                "swap": {"swaps_per_circuit": swaps, "bytes_sent_per_rank_per_circuit": sent,
+                         "exchange_ms_per_circuit": exch_ms / args.steps,
+                         "nvlink_GBps_per_direction": sent / (exch_ms / args.steps * 1e-3) / 1e9 if exch_ms > 0 else None,
+                         "nvlink_peak_GBps_per_direction": 900.0, "detail_first_circuit": stats.detail[:swaps]},
+                "cpu_baseline": None,
+                "e2e": {"value": total_bytes / (e2e_step * 1e-3) / 1e9, "unit": "GB/s",
+                        "h2d_bytes_per_step": sum(op.matrix.nbytes for op in ops), "d2h_bytes_per_step": 72,
+                        "ms_per_step": e2e_step, "amp0": [amps[0].real, amps[0].imag], "norm": nrm},
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,10 +264,17 @@ def main():
     import qsim_b200
 
     torch.cuda.set_device(local_rank)
+    # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO prints a banner there)
+    os.environ["NCCL_DEBUG"] = os.environ.get("QB200_NCCL_DEBUG", "WARN")
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if world > 1:
+        run_sharded(args, rank, world, local_rank, dist)
+        dist.destroy_process_group()
+        return
 
     n, ops = qsim_b200.read_trace(args.trace)
     ss = qsim_b200.StateSpaceB200(np.float32, device=local_rank)
@@ -285,8 +392,6 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks,
                 "timed_region_wall_s": t_wall}
         print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

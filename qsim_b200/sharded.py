@@ -1,0 +1,360 @@
+"""State sharded over 2^g ranks by *global qubits* (one process per GPU,
+torch.distributed for the plumbing, NCCL over NVLink on the GPU box).
+
+Reference precedent: the cuStateVecEx backend's wire ordering + index-bit swaps
+(lib/vectorspace_custatevecex.h:163-177, lib/simulator_custatevecex.h:147-196,
+lib/run_custatevecex.h:243-305).  The policy below is ours (the swaps of the
+reference happen inside the closed cuStateVecEx library).
+
+Layout.  Physical index bit p of an amplitude: p < n_local addresses the
+amplitude inside the rank's shard, p >= n_local is bit (p - n_local) of the rank.
+`pos[q]` is the physical bit that currently holds logical qubit q.  A gate whose
+qubits all sit on local bits is the single-GPU kernel on every shard (matrix
+re-indexed when the physical order differs from the logical one).  A gate that
+touches a global qubit first triggers a local<->global swap:
+
+  1. (local)    victims -- chosen by furthest next use over the remaining gate
+                list -- are moved to the TOP local bits with 2-qubit SWAP passes
+                (HBM-speed, 16*2^n_local bytes each);
+  2. (exchange) the top k local bits are exchanged with k rank bits: the shard
+                splits into 2^k contiguous slices, slice b goes to the peer
+                whose k rank bits equal b and is replaced by that peer's slice
+                (grouped send/recv inside each 2^k-rank group, staged through a
+                bounded transfer buffer).  Bytes sent = bytes received =
+                shard * (1 - 2^-k) per rank.
+
+When a swap is forced, ALL global qubits that are not among the g furthest-used
+qubits are exchanged in the same step (cost grows only as 1 - 2^-k), which is
+what keeps the swap count low on RQCs (see plan_swaps()).
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------
+# planning (pure host logic, no device, no torch)
+# ---------------------------------------------------------------------------
+@dataclass
+class SwapStep:
+    """Before op `before_op`: bring `victims` (logical qubits, currently local) to the
+    top local bits, then exchange them with `incoming` (logical qubits, currently global)."""
+    before_op: int
+    victims: List[int]
+    incoming: List[int]
+
+
+def next_use_table(op_qubits: Sequence[Sequence[int]], num_qubits: int) -> List[Dict[int, int]]:
+    """next_use[i][q] = index of the first op >= i that touches q (len(ops) if none)."""
+    nxt = {q: len(op_qubits) for q in range(num_qubits)}
+    table = [None] * (len(op_qubits) + 1)
+    table[len(op_qubits)] = dict(nxt)
+    for i in range(len(op_qubits) - 1, -1, -1):
+        for q in op_qubits[i]:
+            nxt[q] = i
+        table[i] = dict(nxt)
+    return table
+
+
+def plan_swaps(op_qubits: Sequence[Sequence[int]], num_qubits: int, num_global: int,
+               initial_global: Optional[Sequence[int]] = None) -> List[SwapStep]:
+    """Look-ahead remap pass: Belady-style choice of the global set.
+
+    op_qubits[i] = all qubits (targets and controls) op i touches.  Returns the swap
+    steps; between them every op touches local qubits only."""
+    g = num_global
+    if g == 0:
+        return []
+    glob = list(initial_global) if initial_global is not None else list(range(num_qubits - g, num_qubits))
+    assert len(glob) == g
+    nxt = next_use_table(op_qubits, num_qubits)
+    steps = []
+    for i, qs in enumerate(op_qubits):
+        if len(qs) > num_qubits - g:
+            raise ValueError("gate touches more qubits than a shard holds")
+        if not any(q in glob for q in qs):
+            continue
+        # desired global set: the g qubits whose next use (from op i on) is furthest,
+        # never a qubit of this op; ties broken towards keeping current globals global
+        cand = [q for q in range(num_qubits) if q not in qs]
+        cand.sort(key=lambda q: (-nxt[i][q], 0 if q in glob else 1, q))
+        want = set(cand[:g])
+        incoming = [q for q in glob if q not in want]           # leave the global set
+        victims = [q for q in sorted(want) if q not in glob]    # enter the global set
+        assert len(incoming) == len(victims) and incoming
+        steps.append(SwapStep(i, victims, incoming))
+        glob = [q for q in glob if q in want] + victims
+    return steps
+
+
+def reindex_matrix(matrix: np.ndarray, phys: Sequence[int]) -> Tuple[List[int], np.ndarray]:
+    """Gate matrix given for qubits at physical bits `phys` (bit k of the matrix index
+    <-> phys[k], not necessarily ascending) -> (sorted bits, matrix for sorted order)."""
+    g = len(phys)
+    order = sorted(range(g), key=lambda k: phys[k])
+    if order == list(range(g)):
+        return list(phys), matrix
+    dim = 1 << g
+    m = np.asarray(matrix).reshape(dim, dim, 2) if not np.iscomplexobj(matrix) else np.asarray(matrix).reshape(dim, dim)
+    idx = np.zeros(dim, dtype=np.int64)  # idx[new] = old
+    for new in range(dim):
+        old = 0
+        for j, k in enumerate(order):
+            old |= ((new >> j) & 1) << k
+        idx[new] = old
+    out = m[np.ix_(idx, idx)]
+    return [phys[k] for k in order], np.ascontiguousarray(out).reshape(-1) if not np.iscomplexobj(matrix) else np.ascontiguousarray(out)
+
+
+SWAP_MATRIX = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex64)
+
+
+# ---------------------------------------------------------------------------
+# the sharded simulator (engine-agnostic; the product engine is B200Engine)
+# ---------------------------------------------------------------------------
+class B200Engine:
+    """Local shard on one B200: torch CUDA tensor for the bytes (so torch.distributed
+    can move slices of it), libqsim_b200 kernels for everything else."""
+
+    def __init__(self, n_local: int, device_index: int, dtype=np.float32):
+        import torch
+        from . import backend
+        self.torch = torch
+        self.n_local = n_local
+        self.device = torch.device("cuda", device_index)
+        tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+        self.shard = torch.empty(2 << n_local, dtype=tdt, device=self.device)
+        self.ss = backend.StateSpaceB200(dtype, device=device_index)
+        self.sim = backend.SimulatorB200(dtype, device=device_index)
+        self.state = self.ss.CreateFromPointer(self.shard.data_ptr(), n_local)
+        self._stage = None
+
+    def zero(self):
+        self.ss.SetAllZeros(self.state)
+
+    def set_ampl(self, i, val):
+        self.ss.SetAmpl(self.state, i, val)
+
+    def get_ampl(self, i):
+        return self.ss.GetAmpl(self.state, i)
+
+    def apply_gate(self, qs, matrix):
+        self.sim.ApplyGate(qs, matrix, self.state)
+
+    def apply_controlled_gate(self, qs, cqs, cvals, matrix):
+        self.sim.ApplyControlledGate(qs, cqs, cvals, matrix, self.state)
+
+    def norm(self) -> float:
+        return self.ss.Norm(self.state)
+
+    def slice(self, start_scalar: int, count_scalar: int):
+        return self.shard[start_scalar:start_scalar + count_scalar]
+
+    def staging(self, count_scalar: int):
+        if self._stage is None or self._stage.numel() < count_scalar:
+            self._stage = self.torch.empty(count_scalar, dtype=self.shard.dtype, device=self.device)
+        return self._stage[:count_scalar]
+
+    def sync(self):
+        self.torch.cuda.synchronize(self.device)
+
+    def event(self):
+        """CUDA event recorded on the stream the kernels and the collectives are ordered on."""
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def to_numpy(self):
+        return self.ss.to_numpy(self.state)
+
+
+@dataclass
+class SwapStats:
+    swaps: int = 0
+    local_swap_passes: int = 0
+    bytes_sent: int = 0          # per rank
+    exchange_seconds: float = 0.0
+    detail: List[Tuple[int, int, int]] = field(default_factory=list)  # (before_op, k, bytes)
+
+
+class ShardedSimulator:
+    """n-qubit state over world_size = 2^g ranks.  `engine` holds the local shard,
+    `dist` is torch.distributed (already initialised) or None for a single rank."""
+
+    def __init__(self, num_qubits: int, engine, dist=None, rank: int = 0, world_size: int = 1,
+                 transfer_scalars: int = 1 << 28):
+        g = world_size.bit_length() - 1
+        if 1 << g != world_size:
+            raise ValueError("world_size must be a power of two")
+        if g + 2 > num_qubits:
+            # same guard as lib/multiprocess_custatevecex.h:160-163
+            raise ValueError("too few qubits to shard over this many ranks")
+        self.n, self.g, self.n_local = num_qubits, g, num_qubits - g
+        self.engine, self.dist, self.rank, self.world = engine, dist, rank, world_size
+        self.pos = list(range(num_qubits))       # logical qubit -> physical bit
+        self.transfer_scalars = transfer_scalars  # staging buffer bound per peer piece
+        self.stats = SwapStats()
+        self._exchange_events = []
+
+    # ---- bookkeeping -------------------------------------------------------
+    def global_qubits(self) -> List[int]:
+        return [q for q in range(self.n) if self.pos[q] >= self.n_local]
+
+    def qubit_at(self, phys: int) -> int:
+        return self.pos.index(phys)
+
+    def set_state_zero(self):
+        self.engine.zero()
+        if self.rank == 0:
+            self.engine.set_ampl(0, 1.0)
+
+    # ---- gates ---------------------------------------------------------------
+    def _local_gate(self, qs, cqs, cvals, matrix):
+        phys = [self.pos[q] for q in qs]
+        sorted_bits, m = reindex_matrix(matrix, phys)
+        if cqs:
+            # controls: split into local controls (passed on) and global controls
+            # (decided per rank: the whole shard either qualifies or is skipped)
+            order = sorted(range(len(cqs)), key=lambda k: cqs[k])  # cvals bit i <-> i-th lowest control
+            loc, loc_vals, ok = [], [], True
+            for i, k in enumerate(order):
+                p, v = self.pos[cqs[k]], (cvals >> i) & 1
+                if p >= self.n_local:
+                    ok &= ((self.rank >> (p - self.n_local)) & 1) == v
+                else:
+                    loc.append(p); loc_vals.append(v)
+            if not ok:
+                return
+            if loc:
+                o2 = sorted(range(len(loc)), key=lambda k: loc[k])
+                cv = sum(loc_vals[k] << i for i, k in enumerate(o2))
+                self.engine.apply_controlled_gate(sorted_bits, [loc[k] for k in o2], cv, m)
+                return
+        self.engine.apply_gate(sorted_bits, m)
+
+    def apply_gate(self, qs, matrix, cqs=(), cvals=0):
+        """Applies one gate; every target must currently be local (run() guarantees it)."""
+        if any(self.pos[q] >= self.n_local for q in qs):
+            raise RuntimeError("gate target on a global qubit: call run() or swap first")
+        self._local_gate(list(qs), list(cqs), cvals, matrix)
+
+    # ---- swaps -----------------------------------------------------------------
+    def _local_swap(self, pa: int, pb: int):
+        """exchange two local physical bits with one 2-qubit SWAP pass."""
+        if pa == pb:
+            return
+        lo, hi = min(pa, pb), max(pa, pb)
+        self.engine.apply_gate([lo, hi], SWAP_MATRIX)
+        qa, qb = self.qubit_at(pa), self.qubit_at(pb)
+        self.pos[qa], self.pos[qb] = pb, pa
+        self.stats.local_swap_passes += 1
+
+    def swap(self, victims: Sequence[int], incoming: Sequence[int], before_op: int = -1):
+        """victims: local logical qubits that become global; incoming: global ones that
+        become local.  len(victims) == len(incoming) == k."""
+        import time
+        k = len(victims)
+        assert k == len(incoming) and k >= 1
+        top = list(range(self.n_local - k, self.n_local))
+        # 1. bring the victims to the top k local bits (skip those already there)
+        need = [self.pos[v] for v in victims if self.pos[v] not in top]
+        free_top = [p for p in top if self.qubit_at(p) not in victims]
+        for src, dst in zip(sorted(need), free_top):
+            self._local_swap(src, dst)
+        # 2. exchange top local bit (n_local-k+j) with the rank bit that holds incoming[j]
+        top_q = [self.qubit_at(p) for p in top]                # victim at each top bit
+        gbits = [self.pos[q] - self.n_local for q in incoming]  # rank bit of each incoming qubit
+        slice_scalars = (2 << self.n_local) >> k
+        my = sum(((self.rank >> gb) & 1) << j for j, gb in enumerate(gbits))
+        t0 = time.perf_counter()
+        ev0 = self.engine.event() if hasattr(self.engine, "event") else None
+        if self.dist is not None and self.world > 1:
+            self._exchange(k, gbits, my, slice_scalars)
+        if ev0 is not None:
+            self._exchange_events.append((ev0, self.engine.event()))
+        self.stats.exchange_seconds += time.perf_counter() - t0
+        for j in range(k):
+            self.pos[top_q[j]], self.pos[incoming[j]] = self.n_local + gbits[j], top[j]
+        sent = (slice_scalars * ((1 << k) - 1)) * self.engine.shard.element_size() if hasattr(self.engine, "shard") else 0
+        self.stats.swaps += 1
+        self.stats.bytes_sent += sent
+        self.stats.detail.append((before_op, k, sent))
+
+    def _peer(self, gbits, b):
+        r = self.rank
+        for j, gb in enumerate(gbits):
+            r = (r & ~(1 << gb)) | (((b >> j) & 1) << gb)
+        return r
+
+    def _exchange(self, k, gbits, my, slice_scalars):
+        """slice b of the shard <-> slice `my` of the peer whose selected rank bits equal b.
+        Staged through a bounded buffer: pieces of at most transfer_scalars per peer."""
+        dist = self.dist
+        peers = [(b, self._peer(gbits, b)) for b in range(1 << k) if b != my]
+        piece = min(slice_scalars, self.transfer_scalars)
+        for off in range(0, slice_scalars, piece):
+            cnt = min(piece, slice_scalars - off)
+            stage = self.engine.staging(cnt * len(peers))
+            ops = []
+            for i, (b, peer) in enumerate(peers):
+                send = self.engine.slice(b * slice_scalars + off, cnt)
+                recv = stage[i * cnt:(i + 1) * cnt]
+                ops.append(dist.P2POp(dist.isend, send, peer))
+                ops.append(dist.P2POp(dist.irecv, recv, peer))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for i, (b, peer) in enumerate(peers):
+                self.engine.slice(b * slice_scalars + off, cnt).copy_(stage[i * cnt:(i + 1) * cnt])
+
+    def exchange_device_ms(self) -> float:
+        """device time of all exchanges so far (CUDA events; synchronises)."""
+        if not self._exchange_events:
+            return 0.0
+        self.engine.sync()
+        return float(sum(a.elapsed_time(b) for a, b in self._exchange_events))
+
+    def reset_stats(self):
+        self.stats = SwapStats()
+        self._exchange_events = []
+
+    # ---- whole circuits --------------------------------------------------------
+    def run(self, ops, plan: Optional[List[SwapStep]] = None):
+        """ops: objects with .qubits, .controls, .cvals, .matrix (qsim_b200.trace.TraceOp)."""
+        if plan is None:
+            plan = plan_swaps([list(o.qubits) + list(o.controls) for o in ops], self.n, self.g,
+                              self.global_qubits())
+        steps = {s.before_op: s for s in plan}
+        for i, op in enumerate(ops):
+            if i in steps:
+                self.swap(steps[i].victims, steps[i].incoming, before_op=i)
+            self._local_gate(list(op.qubits), list(op.controls), op.cvals, op.matrix)
+        return plan
+
+    # ---- reductions / access ------------------------------------------------------
+    def norm(self) -> float:
+        v = self.engine.norm()
+        if self.dist is not None and self.world > 1:
+            import torch
+            t = torch.tensor([v], dtype=torch.float64, device=getattr(self.engine, "device", "cpu"))
+            self.dist.all_reduce(t)
+            v = float(t.item())
+        return v
+
+    def locate(self, logical_index: int) -> Tuple[int, int]:
+        """logical amplitude index -> (rank, local index) under the current qubit map."""
+        phys = 0
+        for q in range(self.n):
+            phys |= ((logical_index >> q) & 1) << self.pos[q]
+        return phys >> self.n_local, phys & ((1 << self.n_local) - 1)
+
+    def get_ampl(self, logical_index: int) -> complex:
+        """collective: every rank gets the amplitude."""
+        r, li = self.locate(logical_index)
+        val = self.engine.get_ampl(li) if r == self.rank else 0j
+        if self.dist is not None and self.world > 1:
+            import torch
+            t = torch.tensor([val.real, val.imag], dtype=torch.float64, device=getattr(self.engine, "device", "cpu"))
+            self.dist.all_reduce(t)
+            val = complex(t[0].item(), t[1].item())
+        return val
