@@ -31,7 +31,8 @@ struct Tuning {
   int gate_mode = -1;      // -1 auto; 0 = one amplitude per thread; 1 = two (128-bit)
   int block = 0;           // threads per block override for gate kernels (0 = auto)
   int force_generic = 0;   // 1 = always use the runtime-generic gate kernel
-  int tile = -1;           // -1 auto; 0 = never use the smem-tile kernel; 1 = always when legal
+  int tile = -1;           // -1 auto; 0 = register kernels only; 1 = per-thread cp.async ring only;
+                           // 2 = warp-cooperative tile kernel whenever legal
   int prefetch = -1;       // -1 auto (on); 0 = no software-pipelined persistent loop
 };
 

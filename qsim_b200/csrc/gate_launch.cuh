@@ -4,7 +4,7 @@
 
 #include <cstring>
 
-#include "gate_pipe.cuh"
+#include "gate_tile.cuh"
 
 namespace qb200 {
 
@@ -61,6 +61,30 @@ int launch_pipe(qb200_ctx* ctx, float* st, const Geom& g, const MatParam<float, 
   return QB200_OK;
 }
 
+template <int G, bool PAIR, int TNT, int TD, int TMINB>
+int launch_tile(qb200_ctx* ctx, float* st, const TileGeom& t, const float* m) {
+  MatParam<float, G> mat;
+  mat.fill(m);
+  auto kern = k_gate_tile<G, PAIR, TNT, TD, TMINB>;
+  constexpr size_t smem = tile_smem_bytes<G, TNT, TD>();
+  static const int occ = [&] {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TNT, smem) != cudaSuccess || nb < 1) {
+      (void) cudaGetLastError();
+      nb = 1;
+    }
+    return nb;
+  }();
+  constexpr int warps = TNT / 32;
+  const uint64_t need = (t.work + warps - 1) / warps;
+  const uint64_t persistent = uint64_t{kNumSMs} * occ;
+  const uint32_t blocks = (uint32_t) (need < persistent ? need : persistent);
+  kern<<<blocks, TNT, smem, ctx->stream>>>(st, t, mat);
+  QB_LAUNCHED(ctx);
+  return QB200_OK;
+}
+
 template <typename FP, int G, int MODE, bool EXPECT>
 int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) {
   constexpr int NT = block_threads<FP, G>();
@@ -86,7 +110,7 @@ int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) 
   } else {
     // fp32 G == 4: deep cp.async ring through shared memory (gate_pipe.cuh)
     if constexpr (sizeof(FP) == 4 && G == 4) {
-      if (ctx->tune.tile != 0) {
+      if (ctx->tune.tile != 0) {  // 0 = register kernels only
         switch (ctx->tune.block) {
           case 1: return launch_pipe<G, MODE, 128, (MODE == kV2 ? 3 : 6), 2>(ctx, st, g, mat);
           case 2: return launch_pipe<G, MODE, 256, (MODE == kV2 ? 2 : 4), 1>(ctx, st, g, mat);
@@ -175,6 +199,21 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
     for (unsigned j = 0; j < nc; ++j) bit0_ctrl |= cqs[j] == 0;
     if (nq >= 1 && qs[0] == 0) mode = kV2T;
     else if (!bit0_ctrl && nq <= 4 && nq + nc + 1 <= n) mode = kV2;
+  }
+
+  // fp32 G == 4: warp-cooperative swizzled-tile kernel (gate_tile.cuh) when the lowest
+  // target sits below bit 3 (the per-thread kernels would issue 16-byte chunks at a
+  // 128-byte lane stride there), or everywhere when forced by tuning tile=2.
+  if constexpr (sizeof(FP) == 4 && !EXPECT) {
+    if (!generic && nq == 4 && aligned16 && (ctx->tune.tile == 2 || (ctx->tune.tile == -1 && qs[0] <= 2))) {
+      TileGeom t;
+      int trc = make_tile_geom(n, qs, nq, cqs, nc, cvals, &t);
+      if (trc == QB200_OK) {
+        return t.pair ? launch_tile<4, true, 256, 3, 2>(ctx, st, t, m)
+                      : launch_tile<4, false, 256, 3, 2>(ctx, st, t, m);
+      }
+      if (trc != QB200_ERR_UNSUPPORTED) return trc;
+    }
   }
 
   Geom g;

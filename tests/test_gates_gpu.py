@@ -63,7 +63,8 @@ def test_kernel_variants_agree(oracle, cdt):
     """register kernels (1 and 2 amplitudes per thread) and the runtime-generic
     kernel must all reproduce the oracle."""
     n = 14
-    for variant in ({"gate_mode": 0}, {"force_generic": 1}, {"tile": 0}, {"tile": 1}):
+    for variant in ({"gate_mode": 0}, {"force_generic": 1}, {"tile": 0}, {"tile": 1}, {"tile": 2},
+                    {"tile": 0, "prefetch": 0}, {"tile": 1, "gate_mode": 0}):
         ss, sim = backends(cdt)
         for key, val in variant.items():
             sim.set_tuning(key, val)
@@ -176,3 +177,32 @@ def test_unitarity_round_trip_large():
     got = ss.to_numpy(st)
     assert np.abs(got - amp).max() < 1e-5 * amp * 100
     assert abs(ss.Norm(st) - 1.0) < 1e-5
+
+
+def test_tile_kernel_every_4_qubit_layout(oracle):
+    """warp-cooperative swizzled-tile kernel (gate_tile.cuh): EVERY choice of 4 targets out of 11
+    qubits (330 layouts: all low/high mixes, every swizzle pattern), plus controlled variants."""
+    import qsim_b200
+    ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
+    sim.set_tuning("tile", 2)
+    n = 11
+    host = random_state(n, np.complex64, seed=77)
+    st = ss.Create(n)
+    worst = 0.0
+    for k, qs in enumerate(itertools.combinations(range(n), 4)):
+        m = random_matrix(4, seed=k, cdtype=np.complex64)
+        ss.from_numpy(host, st)
+        sim.ApplyGate(list(qs), m, st)
+        err = np.abs(ss.to_numpy(st) - oracle.apply_gate(host.copy(), list(qs), m)).max()
+        worst = max(worst, err)
+        assert err <= 2e-6, (qs, err)
+    rng = np.random.default_rng(5)
+    for k in range(60):
+        perm = rng.permutation(n)
+        qs, cqs = sorted(perm[:4].tolist()), sorted(perm[4:4 + int(rng.integers(1, 3))].tolist())
+        cvals = int(rng.integers(0, 1 << len(cqs)))
+        m = random_matrix(4, seed=1000 + k, cdtype=np.complex64)
+        ss.from_numpy(host, st)
+        sim.ApplyControlledGate(qs, cqs, cvals, m, st)
+        err = np.abs(ss.to_numpy(st) - oracle.apply_controlled_gate(host.copy(), qs, cqs, cvals, m)).max()
+        assert err <= 2e-6, (qs, cqs, cvals, err)

