@@ -156,7 +156,10 @@ def run_sharded(args, rank, world, local_rank, dist):
     trace = os.path.join(ROOT, "tests", "golden", f"rqc_q{n}_d20_f4.trace")
     nq, ops = qsim_b200.read_trace(trace)
     assert nq == n
-    eng = B200Engine(n - g, local_rank)
+    p2p = os.environ.get("QB200_P2P", "1") == "1"   # 0 = staged NCCL send/recv exchange
+    eng = B200Engine(n - g, local_rank, p2p=p2p)
+    if p2p:
+        eng.connect_peers(dist, rank, world)
     sim = ShardedSimulator(n, eng, dist=dist, rank=rank, world_size=world, transfer_scalars=1 << 28)
     opq = [list(o.qubits) + list(o.controls) for o in ops]
 
@@ -223,8 +226,9 @@ def run_sharded(args, rank, world, local_rank, dist):
                 "config": {"workload": f"rqc_q{n} depth 20 (tools/gen_rqc.py, circuit_q30 rules), max_fused_size 4: {len(ops)} fused-gate "
                                        f"passes on a 2^{n}-amplitude fp32 state sharded over {world} GPUs (8 GiB shard each)",
                            "l2": "shard (8 GiB) is 68x larger than L2",
-                           "multi_gpu": f"global-qubit sharding, {swaps} local<->global swaps per circuit "
-                                        f"(grouped NCCL send/recv), {stats.local_swap_passes // args.steps} local SWAP passes",
+                           "multi_gpu": f"global-qubit sharding, {swaps} local<->global swaps per circuit ("
+                                        + ("one in-place kernel per GPU over NVLink peer memory" if p2p else "grouped NCCL send/recv, staged")
+                                        + f"), {stats.local_swap_passes // args.steps} local SWAP passes",
                            "wall_time_s_per_circuit": ms_per_step * 1e-3},
                 "roofline": {"bound": "hbm", "achieved": value / world, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
                              "frac": value / world / float(peaks["hbm_gbs"]), "traffic": None,

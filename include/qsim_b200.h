@@ -155,6 +155,30 @@ int qb200_collapse(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits,
 int qb200_internal_to_normal_order(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits);
 int qb200_normal_to_internal_order(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits);
 
+/* ---- sharded states: local<->global qubit swap over NVLink peer memory ------ */
+/* A state of n qubits sharded over 2^g GPUs keeps 2^(n-g) amplitudes per GPU; the rank
+ * is the top g index bits.  Exchanging k rank bits with k local bits is the one
+ * collective step of the path.  The reference reaches it only through the closed
+ * cuStateVecEx library (custatevecExStateVectorPermuteIndexBits in
+ * lib/simulator_custatevecex.h:147-196, swaps inside custatevecExSVUpdaterApply,
+ * lib/run_custatevecex.h:243-305); here it is ONE kernel per GPU that reads and writes
+ * the peers' shards directly over NVLink (CUDA IPC mappings), in place, no staging:
+ * each GPU swaps half of every pairwise slice, so both link directions carry
+ * shard*(1-2^-k)/... bytes concurrently.
+ *
+ * qb200_ipc_export / _import / _close: cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle
+ * on a shard allocated by qb200_state_alloc (64-byte opaque handle). */
+int qb200_ipc_export(const void* state, unsigned char handle[64]);
+int qb200_ipc_import(const unsigned char handle[64], void** peer_state);
+int qb200_ipc_close(void* peer_state);
+/* local_bits[j] (ascending, < num_local_qubits) is exchanged with the j-th selected rank
+ * bit; my_value = this rank's value of those k rank bits; peer_states[b] = mapped shard of
+ * the rank whose selected bits equal b (entry my_value ignored).  Every rank of the group
+ * must call it between two stream-ordered barriers. */
+int qb200_swap_global_local(qb200_ctx* ctx, int dtype, void* state, unsigned num_local_qubits,
+                            void* const* peer_states, unsigned k, const unsigned* local_bits,
+                            unsigned my_value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,10 @@ SIGNATURES = {
     "qb200_collapse": (_i, [_vp, _i, _vp, _u, _u64, _u64, _pd]),
     "qb200_internal_to_normal_order": (_i, [_vp, _i, _vp, _u]),
     "qb200_normal_to_internal_order": (_i, [_vp, _i, _vp, _u]),
+    "qb200_ipc_export": (_i, [_vp, C.POINTER(C.c_ubyte)]),
+    "qb200_ipc_import": (_i, [C.POINTER(C.c_ubyte), C.POINTER(_vp)]),
+    "qb200_ipc_close": (_i, [_vp]),
+    "qb200_swap_global_local": (_i, [_vp, _i, _vp, _u, C.POINTER(_vp), _u, _pu, _u]),
 }
 
 _lib = None

@@ -117,18 +117,63 @@ class B200Engine:
     """Local shard on one B200: torch CUDA tensor for the bytes (so torch.distributed
     can move slices of it), libqsim_b200 kernels for everything else."""
 
-    def __init__(self, n_local: int, device_index: int, dtype=np.float32):
+    def __init__(self, n_local: int, device_index: int, dtype=np.float32, p2p: bool = False):
+        """p2p=False: the shard is a torch tensor and swaps go through torch.distributed
+        (grouped NCCL send/recv, staged).  p2p=True: the shard is a cudaMalloc'ed buffer
+        exported with CUDA IPC and swaps are ONE kernel per GPU over NVLink peer memory
+        (qb200_swap_global_local), in place: no staging buffer, no local SWAP passes."""
         import torch
         from . import backend
         self.torch = torch
         self.n_local = n_local
         self.device = torch.device("cuda", device_index)
-        tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
-        self.shard = torch.empty(2 << n_local, dtype=tdt, device=self.device)
+        self.p2p = p2p
+        self.element_size = np.dtype(dtype).itemsize
         self.ss = backend.StateSpaceB200(dtype, device=device_index)
         self.sim = backend.SimulatorB200(dtype, device=device_index)
-        self.state = self.ss.CreateFromPointer(self.shard.data_ptr(), n_local)
+        if p2p:
+            self.shard = None
+            self.state = self.ss.Create(n_local)
+            if self.ss.IsNull(self.state):
+                raise MemoryError("not enough device memory for the shard")
+        else:
+            tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+            self.shard = torch.empty(2 << n_local, dtype=tdt, device=self.device)
+            self.state = self.ss.CreateFromPointer(self.shard.data_ptr(), n_local)
         self._stage = None
+        self._peers = None
+        self._flag = None
+
+    # ---- NVLink peer-memory path ------------------------------------------------
+    def connect_peers(self, dist, rank: int, world: int):
+        """exchange CUDA IPC handles of all shards (once)."""
+        import ctypes as C
+        lib = self.ss._lib
+        h = (C.c_ubyte * 64)()
+        self.ss._check(lib.qb200_ipc_export(self.state.get(), h), "ipc_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h))
+        self._peers = [None] * world
+        for r in range(world):
+            if r == rank:
+                continue
+            hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+            ptr = C.c_void_p()
+            self.ss._check(lib.qb200_ipc_import(hb, C.byref(ptr)), "ipc_import")
+            self._peers[r] = ptr.value
+        self._flag = self.torch.zeros(1, device=self.device)
+
+    def stream_barrier(self, dist):
+        """stream-ordered barrier: no rank's later kernels start before every rank's earlier
+        kernels are done (tiny all-reduce on the kernels' stream; the host does not block)."""
+        dist.all_reduce(self._flag)
+
+    def swap_global_local(self, peer_ranks, k, local_bits, my_value):
+        import ctypes as C
+        arr = (C.c_void_p * (1 << k))(*[self._peers[r] if r is not None else None for r in peer_ranks])
+        lb = (C.c_uint * k)(*local_bits)
+        self.sim._check(self.sim._lib.qb200_swap_global_local(self.sim._ctx, self.sim._dt, self.state.get(),
+                                                              self.n_local, arr, k, lb, my_value), "swap_global_local")
 
     def zero(self):
         self.ss.SetAllZeros(self.state)
@@ -256,6 +301,8 @@ class ShardedSimulator:
         import time
         k = len(victims)
         assert k == len(incoming) and k >= 1
+        if getattr(self.engine, "p2p", False) and self.dist is not None and self.world > 1:
+            return self._swap_p2p(victims, incoming, before_op)
         top = list(range(self.n_local - k, self.n_local))
         # 1. bring the victims to the top k local bits (skip those already there)
         need = [self.pos[v] for v in victims if self.pos[v] not in top]
@@ -276,7 +323,30 @@ class ShardedSimulator:
         self.stats.exchange_seconds += time.perf_counter() - t0
         for j in range(k):
             self.pos[top_q[j]], self.pos[incoming[j]] = self.n_local + gbits[j], top[j]
-        sent = (slice_scalars * ((1 << k) - 1)) * self.engine.shard.element_size() if hasattr(self.engine, "shard") else 0
+        sent = (slice_scalars * ((1 << k) - 1)) * self.engine.shard.element_size() if getattr(self.engine, "shard", None) is not None else 0
+        self.stats.swaps += 1
+        self.stats.bytes_sent += sent
+        self.stats.detail.append((before_op, k, sent))
+
+    def _swap_p2p(self, victims, incoming, before_op):
+        """in-place exchange over NVLink peer memory: the victims' local bits (wherever they
+        are) are swapped with the incoming qubits' rank bits by one kernel per GPU."""
+        k = len(victims)
+        order = sorted(range(k), key=lambda j: self.pos[victims[j]])
+        victims = [victims[j] for j in order]
+        lbits = [self.pos[v] for v in victims]
+        gbits = [self.pos[q] - self.n_local for q in incoming]
+        my = sum(((self.rank >> gb) & 1) << j for j, gb in enumerate(gbits))
+        peers = [None if b == my else self._peer(gbits, b) for b in range(1 << k)]
+        eng = self.engine
+        ev0 = eng.event()
+        eng.stream_barrier(self.dist)
+        eng.swap_global_local(peers, k, lbits, my)
+        eng.stream_barrier(self.dist)
+        self._exchange_events.append((ev0, eng.event()))
+        for j in range(k):
+            self.pos[victims[j]], self.pos[incoming[j]] = self.n_local + gbits[j], lbits[j]
+        sent = ((2 << self.n_local) >> k) * ((1 << k) - 1) * eng.element_size
         self.stats.swaps += 1
         self.stats.bytes_sent += sent
         self.stats.detail.append((before_op, k, sent))

@@ -16,7 +16,10 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 trace = sys.argv[1] if len(sys.argv) > 1 else "tests/golden/q24_d20_f4.trace"
 n, ops = qsim_b200.read_trace(trace)
 g = world.bit_length() - 1
-eng = B200Engine(n - g, local)
+p2p = os.environ.get("QB200_P2P", "1") == "1"
+eng = B200Engine(n - g, local, p2p=p2p)
+if p2p:
+    eng.connect_peers(dist, rank, world)
 sim = ShardedSimulator(n, eng, dist=dist, rank=rank, world_size=world, transfer_scalars=1 << 20)
 sim.set_state_zero()
 plan = sim.run(ops)
@@ -34,7 +37,7 @@ if rank == 0:
         maxerr = max(maxerr, abs(a - ss.GetAmpl(st, i)))
     ok = maxerr < 1e-6 and abs(norm - 1) < 1e-4
     print(json.dumps({"world": world, "n": n, "ops": len(ops), "swaps": sim.stats.swaps, "local_swap_passes": sim.stats.local_swap_passes,
-                      "bytes_sent_per_rank": sim.stats.bytes_sent, "norm": norm, "max_abs_err_vs_single_gpu": maxerr, "ok": ok,
+                      "bytes_sent_per_rank": sim.stats.bytes_sent, "norm": norm, "max_abs_err_vs_single_gpu": maxerr, "ok": ok, "p2p": p2p,
                       "exchange_ms": sim.exchange_device_ms(), "final_global_qubits": sim.global_qubits()}))
 dist.barrier()
 dist.destroy_process_group()
