@@ -34,6 +34,8 @@ struct Tuning {
   int tile = -1;           // -1 auto; 0 = register kernels only; 1 = per-thread cp.async ring only;
                            // 2 = warp-cooperative tile kernel whenever legal
   int prefetch = -1;       // -1 auto (on); 0 = no software-pipelined persistent loop
+  int big = -1;            // -1 auto (on); 0 = fp32 G>=5 through the register/generic kernels;
+                           // 1/2/3 = alternative launch shapes of k_gate_big (tools/microbench.py)
 };
 
 }  // namespace qb200

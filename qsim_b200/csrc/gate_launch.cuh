@@ -13,6 +13,10 @@ int stage_matrix(qb200_ctx* ctx, const void* host, size_t bytes, const void** de
 void stage_matrix_done(qb200_ctx* ctx);
 int finish_expectation(qb200_ctx* ctx, double* partials, uint32_t blocks, double out[2]);
 
+// fp32 G = 5, 6 gate / expectation passes (gate_big.cuh, instantiated in gates_f32_big.cu)
+int launch_big_f32(qb200_ctx* ctx, float* st, const TileGeom& t, unsigned nq, const float* m,
+                   bool expect, double* out);
+
 template <typename FP> struct RegLimits;
 template <> struct RegLimits<float>  { static constexpr int kMaxG = 5; static constexpr int kMaxUnrollG = 4; };
 template <> struct RegLimits<double> { static constexpr int kMaxG = 4; static constexpr int kMaxUnrollG = 3; };
@@ -212,6 +216,16 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
         return t.pair ? launch_tile<4, true, 256, 3, 2>(ctx, st, t, m)
                       : launch_tile<4, false, 256, 3, 2>(ctx, st, t, m);
       }
+      if (trc != QB200_ERR_UNSUPPORTED) return trc;
+    }
+  }
+
+  // fp32 G = 5, 6 (gate and expectation): row-blocked warp-tile kernel (gate_big.cuh)
+  if constexpr (sizeof(FP) == 4) {
+    if (!ctx->tune.force_generic && (nq == 5 || nq == 6) && aligned16 && ctx->tune.big != 0) {
+      TileGeom t;
+      int trc = make_tile_geom(n, qs, nq, cqs, nc, cvals, &t);
+      if (trc == QB200_OK) return launch_big_f32(ctx, st, t, nq, m, EXPECT, out);
       if (trc != QB200_ERR_UNSUPPORTED) return trc;
     }
   }

@@ -1,4 +1,4 @@
-// gate_tile.cuh -- warp-cooperative fused-gate kernel (fp32, G = 4 and 5) for ANY
+// gate_tile.cuh -- warp-cooperative fused-gate kernel (fp32, G = 4; G = 5, 6 in gate_big.cuh) for ANY
 // target layout, including the lowest index bits.
 //
 // Tile.  A warp owns 32 groups whose 2^(G+5) amplitudes form the index set
@@ -26,9 +26,9 @@ namespace qb200 {
 struct TileGeom {
   uint64_t work;        // number of warp tiles
   uint64_t cbits;       // control values at control positions
-  uint64_t goff_m[16];  // global amplitude offset of chunk-row m (lane-independent part)
-  uint32_t sm_m[16];    // swizzled BYTE offset of chunk-row m inside the tile
-  uint32_t skb[32];     // swizzled BYTE offset of group element k
+  uint64_t goff_m[32];  // global amplitude offset of chunk-row m (lane-independent part)
+  uint32_t sm_m[32];    // swizzled BYTE offset of chunk-row m inside the tile
+  uint32_t skb[64];     // swizzled BYTE offset of group element k
   uint32_t npos;        // zero bits inserted to form the tile base ...
   uint8_t pos[44];      // ... at these global positions (B and controls), ascending
   uint8_t bpos[12];     // global bit of tile-local bit i
@@ -163,7 +163,7 @@ constexpr size_t tile_smem_bytes() { return (size_t) (NT / 32) * D * (8 << (G + 
 // use the tile kernel (too few free bits, or bit 0 is a control).
 inline int make_tile_geom(unsigned n, const unsigned* qs, unsigned nq, const unsigned* cqs,
                           unsigned nc, uint64_t cvals, TileGeom* t) {
-  if (n > kMaxQubits || nq > 5 || nq < 1 || nq + nc + 5 > n) return QB200_ERR_UNSUPPORTED;
+  if (n > kMaxQubits || nq > 6 || nq < 1 || nq + nc + 5 > n) return QB200_ERR_UNSUPPORTED;
   uint64_t tmask = 0, cmask = 0;
   for (unsigned j = 0; j < nq; ++j) {
     if (qs[j] >= n || ((tmask >> qs[j]) & 1) || (j > 0 && qs[j] < qs[j - 1])) return QB200_ERR_INVALID;
@@ -214,12 +214,12 @@ inline int make_tile_geom(unsigned n, const unsigned* qs, unsigned nq, const uns
     return o;
   };
   const unsigned rows = 1u << (nq - 1);
-  for (unsigned m = 0; m < 16; ++m) {
+  for (unsigned m = 0; m < 32; ++m) {
     const uint32_t j = m << 6;
     t->goff_m[m] = m < rows ? deposit(j) : 0;
     t->sm_m[m] = m < rows ? swz(j) << 3 : 0;
   }
-  for (unsigned k = 0; k < 32; ++k) {
+  for (unsigned k = 0; k < 64; ++k) {
     uint32_t j = 0;
     for (unsigned b = 0; b < nq; ++b) j |= ((k >> b) & 1u) << tl[b];
     t->skb[k] = k < (1u << nq) ? swz(j) << 3 : 0;

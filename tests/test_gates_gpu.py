@@ -206,3 +206,47 @@ def test_tile_kernel_every_4_qubit_layout(oracle):
         sim.ApplyControlledGate(qs, cqs, cvals, m, st)
         err = np.abs(ss.to_numpy(st) - oracle.apply_controlled_gate(host.copy(), qs, cqs, cvals, m)).max()
         assert err <= 2e-6, (qs, cqs, cvals, err)
+
+
+@pytest.mark.parametrize("g", [5, 6])
+def test_big_kernel_every_layout(oracle, g):
+    """row-blocked warp-tile kernel for 5- and 6-qubit gates (gate_big.cuh): EVERY choice of g
+    targets out of 12 qubits (792 / 924 layouts) for ApplyGate, and every third layout for
+    ExpectationValue; both launch shapes."""
+    import qsim_b200
+    ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
+    n = 12
+    host = random_state(n, np.complex64, seed=g)
+    st = ss.Create(n)
+    for k, qs in enumerate(itertools.combinations(range(n), g)):
+        sim.set_tuning("big", 1 if k % 2 else -1)
+        m = random_matrix(g, seed=k % 17, cdtype=np.complex64)
+        ss.from_numpy(host, st)
+        sim.ApplyGate(list(qs), m, st)
+        err = np.abs(ss.to_numpy(st) - oracle.apply_gate(host.copy(), list(qs), m)).max()
+        assert err <= 4e-6, (qs, err)
+        if k % 3 == 0:
+            ss.from_numpy(host, st)
+            got = sim.ExpectationValue(list(qs), m, st)
+            want = oracle.expectation_value(host, list(qs), m)
+            assert abs(got - want) <= 2e-6 * (1 << g), (qs, got, want)
+            assert np.array_equal(ss.to_numpy(st), host)
+
+
+def test_big_kernel_agrees_with_generic(oracle):
+    """tuning big=0 routes 5/6-qubit gates through the register/generic kernels: same answer."""
+    import qsim_b200
+    ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
+    n = 15
+    host = random_state(n, np.complex64, seed=2)
+    for qs in ([0, 1, 2, 3, 4], [1, 4, 6, 9, 14], [0, 2, 3, 5, 8, 13], [9, 10, 11, 12, 13, 14]):
+        m = random_unitary(len(qs), seed=len(qs), cdtype=np.complex64)
+        outs = []
+        for big in (-1, 0):
+            sim.set_tuning("big", big)
+            st = ss.Create(n)
+            ss.from_numpy(host, st)
+            sim.ApplyGate(qs, m, st)
+            outs.append(ss.to_numpy(st))
+        assert np.abs(outs[0] - outs[1]).max() <= 2e-6, qs
+        assert np.abs(outs[0] - oracle.apply_gate(host.copy(), qs, m)).max() <= 2e-6, qs

@@ -83,7 +83,7 @@ def main():
         med, best = timeit(lambda: sim.ApplyControlledGate(qs, cqs, (1 << len(cqs)) - 1, u, st), args.reps)
         emit({"op": "cgate", "n": n, "G": g, "qs": qs, "cqs": cqs, "ms": med, "GBps": pass_bytes / (1 << len(cqs)) / med / 1e6})
     sim2 = qsim_b200.SimulatorB200(rdt)
-    for g, qs in ((1, [7]), (2, [3, 19]), (4, [8, 9, 14, 15]), (6, [1, 5, 9, 13, 17, 21])):
+    for g, qs in ((1, [7]), (2, [3, 19]), (4, [8, 9, 14, 15]), (5, [0, 3, 7, 12, 20]), (6, [1, 5, 9, 13, 17, 21])):
         if max(qs) >= n:
             continue
         u = unitary(g, g, cdt)
