@@ -1,0 +1,219 @@
+// qsim_qtrajectory_b200 -- BASELINE config 5: Monte-Carlo quantum trajectories of a noisy
+// circuit on the B200 backend, one process per GPU over a slice [traj0, traj0 + n) of the
+// repetition ids (trajectories are independent units: no collective, the observable sums
+// printed by each process are added by the launcher, tools/traj_farm.py).
+//
+// Host side = the reference's own, unchanged, consumed in place from $(QSIM_REF)/lib:
+// CircuitQsimParser, MakeNoisy (lib/circuit_noisy.h:34-96) with DepolarizingChannel
+// (lib/channels_cirq.h:127-200), QuantumTrajectorySimulator::RunOnce (lib/qtrajectory.h),
+// MultiQubitGateFuser, ExpectationValue<IO, Fuser> (lib/expect.h:106-151).
+// Backend = include/qsim_b200/*.h (SimulatorB200 / StateSpaceB200), or -- when compiled with
+// -DQTRAJ_REFERENCE_CPU for the oracle build under oracle/_ref/ -- the reference's CPU
+// simulator selected by lib/simmux.h, so that the same seeds give the same Kraus choices and
+// the observable sums can be compared number by number.
+//
+// Role model: apps/qsim_qtrajectory_cuda.cu (amplitude/phase damping, X observables);
+// here: depolarizing noise after every gate qubit; observables = X_q and Z_q on every qubit
+// plus one 6-qubit Pauli string per window of 6 qubits.
+//
+//   [CUDA_VISIBLE_DEVICES=r] qsim_qtrajectory_b200 -c circuit -d maxtime -p 0.001 -0 traj0 -n num -f 4 [-v 0]
+// prints one JSON line: {"n":..,"traj0":..,"num":..,"seconds":..,"sums":[re,im,...]}
+#include <unistd.h>
+
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "circuit.h"
+#include "channels_cirq.h"
+#include "circuit_noisy.h"
+#include "circuit_qsim_parser.h"
+#include "expect.h"
+#include "fuser_mqubit.h"
+#include "gates_qsim.h"
+#include "io_file.h"
+#include "operation.h"
+#include "qtrajectory.h"
+#include "run_qsim.h"
+
+#ifdef QTRAJ_REFERENCE_CPU
+#include "formux.h"
+#include "simmux.h"
+#else
+#include "qsim_b200/simulator_b200.h"
+#endif
+
+namespace {
+
+struct Options {
+  std::string circuit_file;
+  unsigned maxtime = std::numeric_limits<unsigned>::max();
+  double p = 0.001;
+  unsigned traj0 = 0, num = 8, max_fused_size = 4, verbosity = 0, threads = 0;
+};
+
+Options Parse(int argc, char* argv[]) {
+  Options o;
+  int k;
+  while ((k = getopt(argc, argv, "c:d:p:0:n:f:t:v:")) != -1) {
+    switch (k) {
+      case 'c': o.circuit_file = optarg; break;
+      case 'd': o.maxtime = std::atoi(optarg); break;
+      case 'p': o.p = std::atof(optarg); break;
+      case '0': o.traj0 = std::atoi(optarg); break;
+      case 'n': o.num = std::atoi(optarg); break;
+      case 'f': o.max_fused_size = std::atoi(optarg); break;
+      case 't': o.threads = std::atoi(optarg); break;
+      case 'v': o.verbosity = std::atoi(optarg); break;
+      default:
+        std::fprintf(stderr, "usage: %s -c circuit [-d maxtime] [-p prob] [-0 traj0] [-n num] "
+                             "[-f max_fused_size] [-t threads] [-v verbosity]\n", argv[0]);
+        std::exit(1);
+    }
+  }
+  return o;
+}
+
+// X_q, Z_q for every qubit, then one Pauli string X Z Y X Z Y on each full window of 6 qubits.
+template <typename FP>
+std::vector<std::vector<qsim::OpString<FP>>> Observables(unsigned n) {
+  using namespace qsim;
+  std::vector<std::vector<OpString<FP>>> obs;
+  for (unsigned q = 0; q < n; ++q) obs.push_back({{{1.0, 0.0}, {GateX<FP>::Create(0, q)}}});
+  for (unsigned q = 0; q < n; ++q) obs.push_back({{{1.0, 0.0}, {GateZ<FP>::Create(0, q)}}});
+  for (unsigned w = 0; w + 6 <= n; w += 6) {
+    OpString<FP> s{{1.0, 0.0}, {}};
+    for (unsigned j = 0; j < 6; ++j) {
+      switch (j % 3) {
+        case 0: s.ops.push_back(GateX<FP>::Create(0, w + j)); break;
+        case 1: s.ops.push_back(GateZ<FP>::Create(0, w + j)); break;
+        default: s.ops.push_back(GateY<FP>::Create(0, w + j)); break;
+      }
+    }
+    obs.push_back({s});
+  }
+  return obs;
+}
+
+// Counts the passes the drivers issue (algorithmic HBM bytes of the run):
+// gate pass = 16 * 2^n B, expectation pass = 8 * 2^n B in fp32.
+struct PassCount { uint64_t gates = 0, expects = 0; };
+PassCount g_passes;
+
+template <typename Base>
+struct Counting {
+  using StateSpace = typename Base::StateSpace;
+  using State = typename Base::State;
+  using fp_type = typename Base::fp_type;
+  template <typename... Args>
+  explicit Counting(Args&&... args) : base(std::forward<Args>(args)...) {}
+  void ApplyGate(const std::vector<unsigned>& qs, const fp_type* m, State& s) const {
+    ++g_passes.gates;
+    base.ApplyGate(qs, m, s);
+  }
+  void ApplyControlledGate(const std::vector<unsigned>& qs, const std::vector<unsigned>& cqs, uint64_t cvals,
+                           const fp_type* m, State& s) const {
+    ++g_passes.gates;
+    base.ApplyControlledGate(qs, cqs, cvals, m, s);
+  }
+  std::complex<double> ExpectationValue(const std::vector<unsigned>& qs, const fp_type* m, const State& s) const {
+    ++g_passes.expects;
+    return base.ExpectationValue(qs, m, s);
+  }
+  static unsigned SIMDRegisterSize() { return Base::SIMDRegisterSize(); }
+  Base base;
+};
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+  using namespace qsim;
+  using fp_type = float;
+  const Options opt = Parse(argc, argv);
+
+#ifdef QTRAJ_REFERENCE_CPU
+  struct Factory {
+    using Simulator = Counting<qsim::Simulator<For>>;
+    using StateSpace = Simulator::StateSpace;
+    explicit Factory(unsigned t) : threads(t) {}
+    StateSpace CreateStateSpace() const { return StateSpace(threads); }
+    Simulator CreateSimulator() const { return Simulator(threads); }
+    unsigned threads;
+  };
+  Factory factory(opt.threads ? opt.threads : 1);
+#else
+  struct Factory {
+    using Simulator = Counting<qsim::SimulatorB200<fp_type>>;
+    using StateSpace = Simulator::StateSpace;
+    StateSpace CreateStateSpace() const { return StateSpace(param); }
+    Simulator CreateSimulator() const { return Simulator(); }
+    StateSpace::Parameter param;
+  };
+  Factory factory;  // device: the launcher pins one GPU per process with CUDA_VISIBLE_DEVICES
+#endif
+  using Simulator = Factory::Simulator;
+  using StateSpace = Factory::StateSpace;
+  using Fuser = MultiQubitGateFuser<IO>;
+  using Runner = QSimRunner<IO, Fuser, Factory>;
+  using QTSimulator = QuantumTrajectorySimulator<IO, Runner>;
+
+  Circuit<Operation<fp_type>> circuit;
+  if (opt.circuit_file.empty() ||
+      !CircuitQsimParser<IOFile>::FromFile(opt.maxtime, opt.circuit_file, circuit)) {
+    std::fprintf(stderr, "cannot read circuit\n");
+    return 1;
+  }
+  const auto ncircuit = MakeNoisy(circuit, Cirq::DepolarizingChannel<fp_type>(opt.p));
+  const auto observables = Observables<fp_type>(circuit.num_qubits);
+
+  Simulator simulator = factory.CreateSimulator();
+  StateSpace state_space = factory.CreateStateSpace();
+  auto state = state_space.Create(circuit.num_qubits);
+  if (state_space.IsNull(state)) {
+    std::fprintf(stderr, "not enough memory\n");
+    return 1;
+  }
+
+  typename QTSimulator::Parameter param;
+  param.max_fused_size = opt.max_fused_size;
+  param.verbosity = opt.verbosity;
+  param.apply_last_deferred_ops = true;
+
+  std::vector<std::complex<double>> sums(observables.size(), 0.0);
+  typename QTSimulator::Stat stat;
+
+  // one untimed trajectory: context creation, kernel loading, scratch growth
+  state_space.SetStateZero(state);
+  if (!QTSimulator::RunOnce(param, ncircuit, opt.traj0, state_space, simulator, state, stat)) return 1;
+  (void) ExpectationValue<IO, Fuser>(observables.back(), simulator, state);
+
+  g_passes = PassCount{};
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned i = 0; i < opt.num; ++i) {
+    state_space.SetStateZero(state);
+    // seed = repetition id, as QuantumTrajectorySimulator::RunBatch does (lib/qtrajectory.h:268)
+    if (!QTSimulator::RunOnce(param, ncircuit, uint64_t{opt.traj0} + i, state_space, simulator, state, stat)) {
+      return 1;
+    }
+    for (std::size_t k = 0; k < observables.size(); ++k) {
+      sums[k] += ExpectationValue<IO, Fuser>(observables[k], simulator, state);
+    }
+  }
+  const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+  std::printf("{\"n\": %u, \"traj0\": %u, \"num\": %u, \"num_ops\": %zu, \"num_observables\": %zu, "
+              "\"gate_passes\": %llu, \"expect_passes\": %llu, \"seconds\": %.6f, \"sums\": [",
+              circuit.num_qubits, opt.traj0, opt.num, ncircuit.ops.size(), observables.size(),
+              (unsigned long long) g_passes.gates, (unsigned long long) g_passes.expects, seconds);
+  for (std::size_t k = 0; k < sums.size(); ++k) {
+    std::printf("%s%.9g, %.9g", k ? ", " : "", sums[k].real(), sums[k].imag());
+  }
+  std::printf("]}\n");
+  return 0;
+}

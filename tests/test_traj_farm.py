@@ -1,0 +1,72 @@
+"""Trajectory farm (BASELINE config 5): repetition ids are block-partitioned over
+GPUs and the per-slice observable sums added -- host logic checked on CPU with the reference-CPU
+build of the same driver (oracle/_ref/qsim_qtrajectory_ref) as the worker; on the GPU the B200
+worker must reproduce the reference worker's sums for the same seeds."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from qsim_b200 import traj_farm
+
+REF = os.path.join(traj_farm.ROOT, "oracle", "_ref", "qsim_qtrajectory_ref")
+
+
+def rotation_circuit(n, depth, seed):
+    """qsim-format circuit with generic rotations, so single-qubit expectations are non-trivial."""
+    rng = random.Random(seed)
+    lines = [str(n)]
+    t = 0
+    for d in range(depth):
+        for q in range(n):
+            lines.append(f"{t} {rng.choice(['rx', 'ry', 'rz'])} {q} {rng.uniform(0.2, 2.9):.6f}")
+        t += 1
+        for a in range(d % 2, n - 1, 2):
+            lines.append(f"{t} {rng.choice(['cz', 'is', 'cnot'])} {a} {a + 1}")
+        t += 1
+    return "\n".join(lines) + "\n"
+
+
+@pytest.fixture()
+def circuit_file(tmp_path):
+    p = tmp_path / "rot14"
+    p.write_text(rotation_circuit(14, 5, 7))
+    return str(p)
+
+
+def test_partition_covers_ids_once():
+    for traj0, num, parts in ((0, 8192, 8), (5, 10, 4), (0, 3, 8), (7, 0, 2)):
+        sl = traj_farm.partition(traj0, num, parts)
+        assert len(sl) == parts and sum(c for _, c in sl) == num
+        ids = [i for s, c in sl for i in range(s, s + c)]
+        assert ids == list(range(traj0, traj0 + num))
+        assert max(c for _, c in sl) - min(c for _, c in sl) <= 1
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref not built")
+def test_slices_add_up(circuit_file):
+    one = traj_farm.run_farm(circuit_file, 3, 12, gpus=1, p=0.05, binary=REF, device_ids=[None])
+    four = traj_farm.run_farm(circuit_file, 3, 12, gpus=4, p=0.05, binary=REF, device_ids=[None] * 4)
+    assert four["gpus"] == 4 and four["num"] == 12
+    assert four["gate_passes"] == one["gate_passes"] and four["expect_passes"] == one["expect_passes"]
+    assert np.abs(np.array(one["sums"]) - np.array(four["sums"])).max() < 1e-4
+    # the observables are not trivially zero for this circuit, and the noise matters
+    clean = traj_farm.run_farm(circuit_file, 3, 12, gpus=1, p=0.0, binary=REF, device_ids=[None])
+    assert np.abs(np.array(clean["mean"])).max() > 0.1
+    assert np.abs(np.array(clean["mean"]) - np.array(one["mean"])).max() > 1e-3
+
+
+@pytest.mark.gpu
+def test_b200_trajectories_match_reference_cpu(circuit_file):
+    """same repetition ids => same Kraus choices => same observable sums (fp32 round-off apart)."""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref not built")
+    for fused in (2, 4):
+        ref = traj_farm.run_farm(circuit_file, 0, 16, gpus=1, p=0.05, max_fused_size=fused, binary=REF,
+                                 device_ids=[None])
+        got = traj_farm.run_farm(circuit_file, 0, 16, gpus=1, p=0.05, max_fused_size=fused)
+        assert got["gate_passes"] == ref["gate_passes"] and got["expect_passes"] == ref["expect_passes"]
+        err = np.abs(np.array(got["sums"]) - np.array(ref["sums"])).max()
+        assert err < 16 * 2e-5, err
+        assert np.abs(np.array(ref["mean"])).max() > 0.1

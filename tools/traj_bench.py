@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""BASELINE config 5: 26-qubit depth-20 RQC (tools/gen_rqc.py, circuit_q30 rules) with depolarizing
+noise p=0.001 after every gate qubit; trajectories split over N GPUs; observables X_q, Z_q on every
+qubit + one 6-qubit Pauli string per window.  Prints one JSON line (trajectories/s, aggregate
+algorithmic HBM GB/s).  A bounded sample of the 8192 repetition ids is run (--num per GPU).
+
+  python tools/traj_bench.py --gpus 1 --num 64 [--n 26] [--depth 20] [--fused 4]
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from qsim_b200.traj_farm import run_farm  # noqa: E402
+from tools.gen_rqc import generate  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--gpus", type=int, default=1)
+ap.add_argument("--num", type=int, default=64, help="trajectories per GPU")
+ap.add_argument("--n", type=int, default=26)
+ap.add_argument("--depth", type=int, default=20)
+ap.add_argument("--fused", type=int, default=4)
+ap.add_argument("--p", type=float, default=0.001)
+args = ap.parse_args()
+
+with tempfile.NamedTemporaryFile("w", suffix=f"_rqc_q{args.n}", delete=False) as f:
+    f.write(generate(args.n, args.depth, args.n))
+    path = f.name
+res = run_farm(path, 0, args.num * args.gpus, gpus=args.gpus, p=args.p, max_fused_size=args.fused)
+os.unlink(path)
+res.pop("sums")
+res["mean"] = res["mean"][:8]
+res.update({"config": f"rqc_q{args.n} depth {args.depth}, depolarize p={args.p}, f={args.fused}, "
+                      f"{args.num} of 8192/N trajectories per GPU", "total_repetitions_in_config": 8192,
+            "est_full_8192_s": 8192 / res["trajectories_per_s"]})
+print(json.dumps(res))
