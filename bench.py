@@ -367,8 +367,19 @@ def main():
     peak = float(peaks["hbm_gbs"])
     dom_ms = float(np.mean(g4)) if g4 else float(np.mean([p[2] for p in per_gate]))
     achieved = pass_bytes / (dom_ms * 1e-3) / 1e9
+    # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_g4_traffic.json")) as f:
+            tj = json.load(f)
+        k = tj["kernels"]["k_gate_pipe<4,1,256,2,2>"]
+        traffic = (k["dram_bytes_read"] + k["dram_bytes_write"]) * (amps / float(1 << 30))
+        traffic_src = "profiles/r01_ncu_g4_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_gate_reg<float,4,...> (4-qubit fused gate pass)",
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": pass_bytes,
+                "kernel": "4-qubit fused-gate pass: k_gate_pipe<4,...> (lowest target >= 3) / k_gate_tile<4,...> (lowest target <= 2)",
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                 "avg_launch_ms": dom_ms, "launches_timed": len(g4),
                 "share_of_step": float(np.sum(g4) / np.sum([p[2] for p in per_gate])) if g4 else None,
@@ -385,8 +396,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "circuits/circuit_q30 depth 20, max_fused_size 4: 41 fused-gate passes on a "
-                                       "2^30-amplitude fp32 state (8 GiB) per GPU; trace = reference parser+fuser output",
+                "config": {"workload": f"circuits/circuit_q30 depth 20, {os.path.basename(args.trace)} "
+                                       f"(max_fused_size {os.path.basename(args.trace).split('_f')[-1].split('.')[0]}): {len(ops)} fused-gate passes on a "
+                                       f"2^{n}-amplitude fp32 state ({8 * amps / 2**30:.0f} GiB) per GPU; trace = reference parser+fuser output",
                            "l2": "state (8 GiB) is 68x larger than L2: every pass streams from HBM",
                            "multi_gpu": "independent replicas" if world > 1 else "single GPU",
                            "wall_time_s_per_circuit": ms_per_step * 1e-3},

@@ -17,6 +17,9 @@ int finish_expectation(qb200_ctx* ctx, double* partials, uint32_t blocks, double
 int launch_big_f32(qb200_ctx* ctx, float* st, const TileGeom& t, unsigned nq, const float* m,
                    bool expect, double* out);
 
+// fp32 G = 4, 5 gate passes on the tensor cores (gate_tc.cuh, instantiated in gates_f32_tc.cu)
+int launch_tc_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool pair, const float* m);
+
 template <typename FP> struct RegLimits;
 template <> struct RegLimits<float>  { static constexpr int kMaxG = 5; static constexpr int kMaxUnrollG = 4; };
 template <> struct RegLimits<double> { static constexpr int kMaxG = 4; static constexpr int kMaxUnrollG = 3; };
@@ -203,6 +206,19 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
     for (unsigned j = 0; j < nc; ++j) bit0_ctrl |= cqs[j] == 0;
     if (nq >= 1 && qs[0] == 0) mode = kV2T;
     else if (!bit0_ctrl && nq <= 4 && nq + nc + 1 <= n) mode = kV2;
+  }
+
+  // fp32 G = 4, 5 gates: tcgen05 3xTF32 kernel (gate_tc.cuh); tiles of 128 groups
+  if constexpr (sizeof(FP) == 4 && !EXPECT) {
+    // auto (-1): G = 5 only -- 3.5-3.7 ms against 5.95 ms on the CUDA cores at n = 30; the G = 4
+    // tensor-core pass (3.35 ms) still loses to the cp.async FFMA2 kernel (2.8-3.0 ms)
+    const bool use_tc = ctx->tune.tc > 0 || (ctx->tune.tc < 0 && nq == 5);
+    if (!ctx->tune.force_generic && (nq == 4 || nq == 5) && aligned16 && use_tc && n >= nq + nc + 7) {
+      Geom tg;
+      int trc = make_geom(n, qs, nq, cqs, nc, cvals, false, &tg);
+      if (trc) return trc;
+      return launch_tc_f32(ctx, st, tg, nq, qs[0] == 0, m);
+    }
   }
 
   // fp32 G == 4: warp-cooperative swizzled-tile kernel (gate_tile.cuh) when the lowest

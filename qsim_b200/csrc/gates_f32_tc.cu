@@ -1,0 +1,59 @@
+// gates_f32_tc.cu -- instantiates and launches the tcgen05 (3xTF32) gate kernels (gate_tc.cuh).
+#include <cstdio>
+#include <cstdlib>
+
+#include "gate_tc.cuh"
+#include "gate_launch.cuh"
+
+namespace qb200 {
+
+namespace {
+
+template <int G, bool PAIR, int NBUF, int PF, int MINB>
+int launch_tc_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
+  auto kern = k_gate_tc<G, PAIR, NBUF, PF, MINB>;
+  constexpr size_t smem = tc_smem_bytes<G, NBUF>();
+  static const int occ = [&] {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // resident CTAs per SM: shared memory (227 KB usable, 1 KB reserved per CTA) and TMEM
+    // (512 columns) are the limits; the runtime's occupancy query answers 1 for kernels that
+    // allocate tensor memory, so it is not used here
+    int nb = (int) ((227 * 1024) / (smem + 1024 + 64));
+    const int tmem_limit = 512 / (NBUF * TcShape<G>::KF);
+    if (nb > tmem_limit) nb = tmem_limit;
+    if (nb > MINB) nb = MINB;
+    if (nb < 1) nb = 1;
+    if (getenv("QB200_VERBOSE")) fprintf(stderr, "k_gate_tc<%d>: smem %zu, blocks per SM %d\n", G, smem, nb);
+    return nb;
+  }();
+  MatParam<float, G> mat;
+  mat.fill(m);
+  const uint64_t tiles = g.work >> 7;
+  const uint64_t persistent = uint64_t{kNumSMs} * occ;
+  const uint32_t blocks = (uint32_t) (tiles < persistent ? tiles : persistent);
+  kern<<<blocks, kTcThreads, smem, ctx->stream>>>(st, g, mat);
+  QB_LAUNCHED(ctx);
+  return QB200_OK;
+}
+
+}  // namespace
+
+int launch_tc_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool pair, const float* m) {
+  const bool alt = ctx->tune.tc == 2;  // alternative shapes (tools/tc_check.py)
+  if (nq == 4) {
+    if (alt) {
+      return pair ? launch_tc_shape<4, true, 1, 2, 4>(ctx, st, g, m) : launch_tc_shape<4, false, 1, 2, 4>(ctx, st, g, m);
+    }
+    return pair ? launch_tc_shape<4, true, 2, 2, 3>(ctx, st, g, m) : launch_tc_shape<4, false, 2, 2, 3>(ctx, st, g, m);
+  }
+  if (nq == 5) {
+    if (alt) {
+      return pair ? launch_tc_shape<5, true, 2, 2, 1>(ctx, st, g, m) : launch_tc_shape<5, false, 2, 2, 1>(ctx, st, g, m);
+    }
+    return pair ? launch_tc_shape<5, true, 1, 1, 2>(ctx, st, g, m) : launch_tc_shape<5, false, 1, 1, 2>(ctx, st, g, m);
+  }
+  return QB200_ERR_UNSUPPORTED;
+}
+
+}  // namespace qb200
