@@ -30,6 +30,16 @@ TRACE = os.path.join(ROOT, "tests", "golden", "q30_d20_f4.trace")
 METRIC = "rqc_q30_d20_f4_fused_gate_hbm_gbs"
 
 
+# stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner,
+# torchrun notices) is sent to stderr by pointing fd 1 at fd 2 for the whole run.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -139,7 +149,7 @@ def run_reference_arm(args, rank):
                        "l2": "state (8 GiB) far larger than any cache"},
             "cpu_baseline": res,
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_sharded(args, rank, world, local_rank, dist):
@@ -152,7 +162,7 @@ def run_sharded(args, rank, world, local_rank, dist):
     from qsim_b200.sharded import B200Engine, ShardedSimulator, plan_swaps
 
     g = world.bit_length() - 1
-    n = 30 + g
+    n = args.shard_qubits + g
     trace = os.path.join(ROOT, "tests", "golden", f"rqc_q{n}_d20_f4.trace")
     nq, ops = qsim_b200.read_trace(trace)
     assert nq == n
@@ -224,8 +234,8 @@ def run_sharded(args, rank, world, local_rank, dist):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"rqc_q{n} depth 20 (tools/gen_rqc.py, circuit_q30 rules), max_fused_size 4: {len(ops)} fused-gate "
-                                       f"passes on a 2^{n}-amplitude fp32 state sharded over {world} GPUs (8 GiB shard each)",
-                           "l2": "shard (8 GiB) is 68x larger than L2",
+                                       f"passes on a 2^{n}-amplitude fp32 state sharded over {world} GPUs ({8 << (n - g - 30)} GiB shard each)",
+                           "l2": f"shard ({8 << (n - g - 30)} GiB) is far larger than L2",
                            "multi_gpu": f"global-qubit sharding, {swaps} local<->global swaps per circuit ("
                                         + ("one in-place kernel per GPU over NVLink peer memory" if p2p else "grouped NCCL send/recv, staged")
                                         + f"), {stats.local_swap_passes // args.steps} local SWAP passes",
@@ -243,7 +253,7 @@ def run_sharded(args, rank, world, local_rank, dist):
                         "h2d_bytes_per_step": sum(op.matrix.nbytes for op in ops), "d2h_bytes_per_step": 72,
                         "ms_per_step": e2e_step, "amp0": [amps[0].real, amps[0].imag], "norm": nrm},
                 "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line))
+        emit(line)
 
 
 def main():
@@ -254,6 +264,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace", default=TRACE)
+    ap.add_argument("--shard-qubits", type=int, default=30,
+                    help="N > 1 only: qubits per shard (30 = 8 GiB, the driver's weak-scaling point; "
+                         "34 = 128 GiB: BASELINE config 4, 36 qubits on 4 GPUs / 37 on 8)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -407,7 +420,7 @@ def main():
                         "ms_per_step": e2e_step, "amp0": [amp_out[0].real, amp_out[0].imag], "norm": nrm},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "timed_region_wall_s": t_wall}
-        print(json.dumps(line))
+        emit(line)
 
 
 if __name__ == "__main__":

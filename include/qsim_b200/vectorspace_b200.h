@@ -59,6 +59,16 @@ inline void free(void* ptr) { qb200_state_free(ptr); }
 
 }  // namespace b200
 
+// lib/vectorspace_cuda.h:31-39 publishes its deleter as qsim::detail::free and the pybind layer
+// names it (pybind_interface/pybind_main.cpp:455); a backend header provides it, exactly one
+// backend header per translation unit (the reference's CPU and CUDA headers clash the same way).
+#if !defined(VECTORSPACE_H_) && !defined(VECTORSPACE_CUDA_H_)
+namespace detail {
+inline void do_not_free(void*) {}
+inline void free(void* ptr) { qb200_state_free(ptr); }
+}  // namespace detail
+#endif
+
 template <typename Impl, typename FP>
 class VectorSpaceB200 {
  public:

@@ -214,18 +214,31 @@ k_gate_tc(float* __restrict__ st, const __grid_constant__ Geom g,
   const uint32_t row_off = (row >> 3) * 1024 + (row & 7) * 128;
   const uint32_t row_x = row & 7;
   const int k0 = (int) half * HN;  // first amplitude of this thread's half row
-  // k0 is 0 or HN = 2^(G-1): elem_offset(k0 + j) = half * xs[G-1] + elem_offset(j) for j < HN
-  const uint64_t half_off = half ? g.xs[G - 1] : 0;
+  // Addressing, hoisted out of the tile loop (it was ~2/3 of all issued instructions):
+  //   amplitude index of (tile, row, element k0 + j) = dep(tile << 7) | dep(row) | cbits + half * xs[G-1] + eo(j)
+  // dep() deposits index bits at the free positions; the 7 row bits take the 7 lowest free ones, so
+  // the two deposits are disjoint and the row part is a per-thread constant.
+  const uint64_t thread_off = 8 * (expand_index(row, g) + (half ? g.xs[G - 1] : 0));  // bytes, includes cbits
+  unsigned char* const st_b = reinterpret_cast<unsigned char*>(st);
+  auto tile_ptr = [&](uint64_t tile) {  // warp-uniform part, evaluated on the uniform datapath
+    uint64_t i = tile << 7;
+    for (uint32_t k = 0; k < g.npos; ++k) {
+      const uint64_t lo = i & ((uint64_t{1} << g.pos[k]) - 1);
+      i = ((i - lo) << 1) | lo;
+    }
+    return st_b + 8 * i + thread_off;
+  };
+  auto eo = [&](int j) { return 8 * elem_offset<G>(j, g); };  // byte offset of element j, uniform
 
   auto load_mine = [&](uint64_t tile, uint4 (&x)[CHUNKS]) {
-    const float* p = st + 2 * (expand_index((tile << 7) + row, g) + half_off);
+    const unsigned char* const p = tile_ptr(tile);
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
       if constexpr (PAIR) {
-        x[c] = *reinterpret_cast<const uint4*>(p + 2 * elem_offset<G>(2 * c, g));
+        x[c] = *reinterpret_cast<const uint4*>(p + eo(2 * c));
       } else {
-        const uint2 a = *reinterpret_cast<const uint2*>(p + 2 * elem_offset<G>(2 * c, g));
-        const uint2 b = *reinterpret_cast<const uint2*>(p + 2 * elem_offset<G>(2 * c + 1, g));
+        const uint2 a = *reinterpret_cast<const uint2*>(p + eo(2 * c));
+        const uint2 b = *reinterpret_cast<const uint2*>(p + eo(2 * c + 1));
         x[c] = make_uint4(a.x, a.y, b.x, b.y);
       }
     }
@@ -276,14 +289,14 @@ k_gate_tc(float* __restrict__ st, const __grid_constant__ Geom g,
   };
 
   auto store_mine = [&](uint64_t tile, const uint32_t (&v)[N]) {
-    float* const p = st + 2 * (expand_index((tile << 7) + row, g) + half_off);
+    unsigned char* const p = tile_ptr(tile);
 #pragma unroll
     for (int j = 0; j < HN; j += (PAIR ? 2 : 1)) {
       if constexpr (PAIR) {
-        *reinterpret_cast<uint4*>(p + 2 * elem_offset<G>(j, g)) =
+        *reinterpret_cast<uint4*>(p + eo(j)) =
             make_uint4(v[2 * j], v[2 * j + 1], v[2 * j + 2], v[2 * j + 3]);
       } else {
-        *reinterpret_cast<uint2*>(p + 2 * elem_offset<G>(j, g)) = make_uint2(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint2*>(p + eo(j)) = make_uint2(v[2 * j], v[2 * j + 1]);
       }
     }
   };
@@ -307,14 +320,6 @@ k_gate_tc(float* __restrict__ st, const __grid_constant__ Geom g,
       }
     }
     split_store(cur, b);  // NBUF == 2: buffer b was released by the wait of iteration it-1
-    // Prefetch AFTER the last use of `cur`: LDG results are tracked by counting scoreboards, so a
-    // consumer placed behind younger loads waits for those too -- loads issued before the split
-    // would be waited for in the same iteration (measured: no prefetch effect at all).
-    if constexpr (PF == 2) {
-      if (tile + 2 * stride < ntiles) load_mine(tile + 2 * stride, nx2);
-    } else {
-      if (tile + stride < ntiles) load_mine(tile + stride, nxt);
-    }
     tc::fence_async_smem();
     tc::fence_before();
     __syncthreads();
@@ -326,6 +331,14 @@ k_gate_tc(float* __restrict__ st, const __grid_constant__ Geom g,
         issue_mmas(b, smem_u32(&mbar[b]));
       }
       __syncwarp();
+    }
+    // Prefetch for the following tiles, issued AFTER the proxy fence and the barrier: a fence
+    // completes only when the thread's earlier memory operations have, so loads issued in front
+    // of it would be waited for right there (measured: no prefetch effect at all).
+    if constexpr (PF == 2) {
+      if (tile + 2 * stride < ntiles) load_mine(tile + 2 * stride, nx2);
+    } else {
+      if (tile + stride < ntiles) load_mine(tile + stride, nxt);
     }
     if (it > 0) {
       if constexpr (NBUF == 2) {

@@ -227,6 +227,8 @@ class ShardedSimulator:
     """n-qubit state over world_size = 2^g ranks.  `engine` holds the local shard,
     `dist` is torch.distributed (already initialised) or None for a single rank."""
 
+    MIN_SWAP_BIT = 4  # victims below this local bit are moved up before the peer-memory exchange
+
     def __init__(self, num_qubits: int, engine, dist=None, rank: int = 0, world_size: int = 1,
                  transfer_scalars: int = 1 << 28):
         g = world_size.bit_length() - 1
@@ -332,6 +334,17 @@ class ShardedSimulator:
         """in-place exchange over NVLink peer memory: the victims' local bits (wherever they
         are) are swapped with the incoming qubits' rank bits by one kernel per GPU."""
         k = len(victims)
+        # The kernel moves 16-byte items; a swapped local bit b makes contiguous runs of 2^b
+        # amplitudes, and NVLink wants >= 256-byte runs: 695 GB/s per direction for b >= 5,
+        # 503 at b = 3, 392 at b = 2 (tools/swap_bench.py).  A victim sitting on one of the
+        # lowest bits is first moved up by one local SWAP pass (2.5 ms per 8 GiB shard).
+        taken = {self.pos[v] for v in victims}
+        for v in victims:
+            if self.pos[v] < self.MIN_SWAP_BIT:
+                dst = next(p for p in range(self.n_local - 1, self.MIN_SWAP_BIT - 1, -1) if p not in taken)
+                taken.discard(self.pos[v])
+                self._local_swap(self.pos[v], dst)
+                taken.add(dst)
         order = sorted(range(k), key=lambda j: self.pos[victims[j]])
         victims = [victims[j] for j in order]
         lbits = [self.pos[v] for v in victims]
