@@ -119,6 +119,41 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
+// tcgen05.st: 16 / 32 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]: A is M x K with rows on TMEM lanes and K along 32-bit columns
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // hi = x rounded to nearest tf32 (10-bit mantissa), exact as an fp32 bit pattern
 __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
@@ -358,6 +393,216 @@ k_gate_tc(float* __restrict__ st, const __grid_constant__ Geom g,
     uint32_t v[N];
     wait_tile(it - 1);
     tc::tmem_ld(tmem_mine + ((it - 1) % NBUF) * KF, v);
+    store_mine(prev_tile, v);
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Variant with the A operand in TENSOR MEMORY.  The split halves of the state tile never touch
+// shared memory: each thread tcgen05.st's the hi and lo halves of its half row into its own TMEM
+// lane, the MMAs read A from TMEM (tcgen05.mma [d], [a], b-desc) and only W (a few KB) comes from
+// shared memory.  No generic->async proxy fence per tile, no operand traffic on the shared-memory
+// port, no operand buffers in shared memory (residency is bounded by TMEM columns alone).
+// TMEM columns of buffer b: [A_hi KF][A_lo KF][D KF].
+// ---------------------------------------------------------------------------------------------
+template <int G, int NBUF>
+__host__ __device__ constexpr int tca_tmem_cols() {
+  const int need = NBUF * 3 * TcShape<G>::KF;
+  return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+}
+template <int G>
+constexpr size_t tca_smem_bytes() { return 1024 + 2 * TcShape<G>::B_TILE; }
+
+template <int G, bool PAIR, int NBUF, int PF, int MINB>
+__global__ void __launch_bounds__(kTcThreads, MINB)
+k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
+           const __grid_constant__ MatParam<float, G> mat) {
+  using S = TcShape<G>;
+  constexpr int N = S::N, KF = S::KF, HN = N / 2;
+  constexpr int CHUNKS = HN / 2;
+  constexpr int TCOLS = tca_tmem_cols<G, NBUF>();
+  static_assert(NBUF == 1 || NBUF == 2, "one or two operand/accumulator buffers");
+  static_assert(NBUF * 3 * KF <= 512, "tensor memory has 512 columns");
+  extern __shared__ unsigned char tc_raw[];
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t t = threadIdx.x;
+  const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const uint32_t row = t & 127, half = t >> 7;
+  const uint32_t raw_s = smem_u32(tc_raw);
+  const uint32_t base_s = (raw_s + 1023u) & ~1023u;
+  unsigned char* const base_p = tc_raw + (base_s - raw_s);
+  const uint32_t bhi_s = base_s, blo_s = base_s + S::B_TILE;
+  unsigned char* const bhi_p = base_p;
+  unsigned char* const blo_p = base_p + S::B_TILE;
+
+  for (uint32_t idx = t; idx < (uint32_t) (KF * KF); idx += kTcThreads) {
+    const uint32_t n = idx / KF, k = idx % KF;
+    const uint32_t r = n >> 1, c = k >> 1;
+    const float ur = mat.m[2 * (r * N + c)], ui = mat.m[2 * (r * N + c) + 1];
+    const float w = (n & 1) ? ((k & 1) ? ur : ui) : ((k & 1) ? -ui : ur);
+    const float hi = tc::tf32_hi(w);
+    const uint32_t off = (k >> 5) * S::B_ATOM + sw128_off(n, (k & 31) >> 2) + (k & 3) * 4;
+    *reinterpret_cast<float*>(bhi_p + off) = hi;
+    *reinterpret_cast<float*>(blo_p + off) = w - hi;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "n"(TCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (t == 0) {
+    tc::mbar_init(smem_u32(&mbar[0]), 1);
+    tc::mbar_init(smem_u32(&mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc::fence_async_smem();  // W was written through the generic proxy, the MMAs read it through the async proxy
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
+  // this thread's lane (its row) and its half of the K / N columns inside a [KF]-wide block
+  const uint32_t tmem_mine = tmem_base + (((warp & 3) * 32u) << 16) + half * N;
+  constexpr uint32_t idesc = tc::instr_desc_tf32(KF);
+
+  const uint64_t ntiles = g.work >> 7;
+  const uint64_t stride = gridDim.x;
+
+  const uint64_t thread_off = 8 * (expand_index(row, g) + (half ? g.xs[G - 1] : 0));
+  unsigned char* const st_b = reinterpret_cast<unsigned char*>(st);
+  auto tile_ptr = [&](uint64_t tile) {
+    uint64_t i = tile << 7;
+    for (uint32_t k = 0; k < g.npos; ++k) {
+      const uint64_t lo = i & ((uint64_t{1} << g.pos[k]) - 1);
+      i = ((i - lo) << 1) | lo;
+    }
+    return st_b + 8 * i + thread_off;
+  };
+  auto eo = [&](int j) { return 8 * elem_offset<G>(j, g); };
+
+  auto load_mine = [&](uint64_t tile, uint4 (&x)[CHUNKS]) {
+    const unsigned char* const p = tile_ptr(tile);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      if constexpr (PAIR) {
+        x[c] = *reinterpret_cast<const uint4*>(p + eo(2 * c));
+      } else {
+        const uint2 a = *reinterpret_cast<const uint2*>(p + eo(2 * c));
+        const uint2 b = *reinterpret_cast<const uint2*>(p + eo(2 * c + 1));
+        x[c] = make_uint4(a.x, a.y, b.x, b.y);
+      }
+    }
+  };
+
+  // hi/lo split in registers, written to this thread's TMEM lane: columns [A_hi | A_lo] of buffer b
+  auto split_to_tmem = [&](const uint4 (&x)[CHUNKS], int b) {
+    uint32_t h[N], l[N];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const uint32_t w[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xf = __uint_as_float(w[e]);
+        const float hf = tc::tf32_hi(xf);
+        h[4 * c + e] = __float_as_uint(hf);
+        l[4 * c + e] = __float_as_uint(xf - hf);
+      }
+    }
+    tc::tmem_st(tmem_mine + b * 3 * KF, h);
+    tc::tmem_st(tmem_mine + b * 3 * KF + KF, l);
+    tc::tmem_st_wait();
+  };
+
+  auto issue_mmas = [&](int b, uint32_t mb) {
+    tc::fence_after();
+    const uint32_t ahi = tmem_base + b * 3 * KF, alo = ahi + KF, d = ahi + 2 * KF;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {
+      const uint32_t ab = term == 0 ? alo : ahi;
+      const uint32_t bb = term == 1 ? blo_s : bhi_s;
+#pragma unroll
+      for (int k = 0; k < KF / 8; ++k) {
+        const uint64_t bd = tc::smem_desc_sw128(bb + (k >> 2) * S::B_ATOM + (k & 3) * 32);
+        tc::mma_tf32_ts(d, ab + 8 * k, bd, idesc, acc);
+        acc = 1;
+      }
+    }
+    tc::mma_commit(mb);
+  };
+
+  auto wait_tile = [&](uint32_t i) {
+    tc::mbar_wait(smem_u32(&mbar[i % NBUF]), (i / NBUF) & 1);
+    tc::fence_after();
+  };
+
+  auto store_mine = [&](uint64_t tile, const uint32_t (&v)[N]) {
+    unsigned char* const p = tile_ptr(tile);
+#pragma unroll
+    for (int j = 0; j < HN; j += (PAIR ? 2 : 1)) {
+      if constexpr (PAIR) {
+        *reinterpret_cast<uint4*>(p + eo(j)) = make_uint4(v[2 * j], v[2 * j + 1], v[2 * j + 2], v[2 * j + 3]);
+      } else {
+        *reinterpret_cast<uint2*>(p + eo(j)) = make_uint2(v[2 * j], v[2 * j + 1]);
+      }
+    }
+  };
+
+  static_assert(PF == 1 || PF == 2, "prefetch one or two tiles ahead");
+  uint4 cur[CHUNKS], nxt[CHUNKS], nx2[PF == 2 ? CHUNKS : 1];
+  uint64_t tile = blockIdx.x, prev_tile = 0;
+  if (tile < ntiles) load_mine(tile, cur);
+  if constexpr (PF == 2) {
+    if (tile + stride < ntiles) load_mine(tile + stride, nxt);
+  }
+  uint32_t it = 0;
+  for (; tile < ntiles; tile += stride, ++it) {
+    const int b = it % NBUF;
+    uint32_t v[N];
+    if constexpr (NBUF == 1) {
+      if (it > 0) {
+        wait_tile(it - 1);
+        tc::tmem_ld(tmem_mine + 2 * KF, v);
+      }
+    }
+    split_to_tmem(cur, b);
+    if constexpr (PF == 2) {
+      if (tile + 2 * stride < ntiles) load_mine(tile + 2 * stride, nx2);
+    } else {
+      if (tile + stride < ntiles) load_mine(tile + stride, nxt);
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      if (tc::elect_one()) issue_mmas(b, smem_u32(&mbar[b]));
+      __syncwarp();
+    }
+    if (it > 0) {
+      if constexpr (NBUF == 2) {
+        wait_tile(it - 1);
+        tc::tmem_ld(tmem_mine + ((it - 1) & 1) * 3 * KF + 2 * KF, v);
+      }
+      store_mine(prev_tile, v);
+    }
+    prev_tile = tile;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      cur[c] = nxt[c];
+      if constexpr (PF == 2) nxt[c] = nx2[c];
+    }
+  }
+  if (it > 0) {
+    uint32_t v[N];
+    wait_tile(it - 1);
+    tc::tmem_ld(tmem_mine + ((it - 1) % NBUF) * 3 * KF + 2 * KF, v);
     store_mine(prev_tile, v);
   }
   tc::fence_before();

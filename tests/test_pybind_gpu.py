@@ -27,6 +27,7 @@ def load_module():
 
 H = (np.array([[1, 1], [1, -1]]) / np.sqrt(2)).astype(np.complex64)
 CZ = np.diag([1, 1, 1, -1]).astype(np.complex64)
+BE2 = [0, 2, 1, 3]
 
 
 def build(q, n, oracle):
@@ -48,7 +49,9 @@ def build(q, n, oracle):
             if layer % 2 == 0:
                 u = random_unitary(2, 100 * layer + j, np.complex64)
                 q.add_matrix_gate(t, qs, np.ascontiguousarray(u).view(np.float32).ravel().tolist(), c)
-                oracle.apply_gate(want, qs, u)
+                # Cirq matrices are big-endian in the gate's qubits (gates_cirq.h: MatrixGate2, q0 = MSB);
+                # the engine's convention is bit k of the matrix index <-> qs[k]
+                oracle.apply_gate(want, qs, np.ascontiguousarray(u[BE2][:, BE2]))
             else:
                 q.add_gate(q.GateKind.kCZ, t, qs, {}, c)
                 oracle.apply_gate(want, qs, CZ)
