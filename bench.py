@@ -264,6 +264,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace", default=TRACE)
+    ap.add_argument("--tune", action="append", default=[], help="key=value tuning override (N = 1), e.g. tc=0")
     ap.add_argument("--shard-qubits", type=int, default=30,
                     help="N > 1 only: qubits per shard (30 = 8 GiB, the driver's weak-scaling point; "
                          "34 = 128 GiB: BASELINE config 4, 36 qubits on 4 GPUs / 37 on 8)")
@@ -296,6 +297,9 @@ def main():
     n, ops = qsim_b200.read_trace(args.trace)
     ss = qsim_b200.StateSpaceB200(np.float32, device=local_rank)
     sim = qsim_b200.SimulatorB200(np.float32, device=local_rank)
+    for kv in args.tune:
+        key, val = kv.split("=")
+        sim.set_tuning(key, int(val))
     st = ss.Create(n)
     if ss.IsNull(st):
         raise SystemExit("not enough device memory for the state")
@@ -368,36 +372,54 @@ def main():
         e2e_step = float(t.item())
     e2e_value = total_bytes / (e2e_step * 1e-3) / 1e9
 
-    # ---- per-launch durations of the dominant kernel (4-qubit fused gate) ----
+    # ---- per-launch durations, grouped by the kernel the dispatcher picks (gate_launch.cuh) ----
     ss.SetStateZero(st)
     per_gate = []
     for op in ops:
         sim.timer_start()
         sim.ApplyGate(op.qubits, op.matrix, st)
-        per_gate.append((len(op.qubits), op.qubits[0], sim.timer_stop_ms()))
-    g4 = [ms for g, q0, ms in per_gate if g == 4]
+        per_gate.append((len(op.qubits), list(op.qubits), sim.timer_stop_ms()))
+    tc_off = any(kv.replace(" ", "") == "tc=0" for kv in args.tune)
+
+    def kernel_class(g, qs):
+        low_t = qs[1] if g >= 2 and qs[0] == 0 else (qs[0] if g else 0)
+        if g == 5:
+            return "k_gate_big<5> (FFMA2)" if tc_off else "k_gate_tca<5> (tcgen05 3xTF32, A in TMEM)"
+        if g == 4:
+            if not tc_off and low_t >= 4:
+                return "k_gate_tca<4> (tcgen05 3xTF32, A in TMEM)"
+            return "k_gate_tile<4> (FFMA2, warp tile)" if qs[0] <= 2 else "k_gate_pipe<4> (FFMA2, cp.async ring)"
+        return f"k_gate_reg<{g}> (FFMA2)" if g < 6 else "k_gate_big<6> (FFMA2)"
+
+    classes = {}
+    for g, qs, ms in per_gate:
+        classes.setdefault(kernel_class(g, qs), []).append(ms)
+    total_ms = float(np.sum([p[2] for p in per_gate]))
+    kernels = {k: {"launches": len(v), "avg_ms": float(np.mean(v)), "GBps": pass_bytes / (float(np.mean(v)) * 1e-3) / 1e9,
+                   "share_of_step": float(np.sum(v)) / total_ms} for k, v in classes.items()}
+    dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
     peaks, peak_kind = measured_peaks()
     peak = float(peaks["hbm_gbs"])
-    dom_ms = float(np.mean(g4)) if g4 else float(np.mean([p[2] for p in per_gate]))
+    dom_ms = kernels[dom]["avg_ms"]
     achieved = pass_bytes / (dom_ms * 1e-3) / 1e9
     # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture
     traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_ncu_g4_traffic.json")) as f:
             tj = json.load(f)
-        k = tj["kernels"]["k_gate_pipe<4,1,256,2,2>"]
+        key = next(k for k in tj["kernels"] if dom.startswith(k.split("<")[0]) and k.split("<")[1][0] == dom.split("<")[1][0])
+        k = tj["kernels"][key]
         traffic = (k["dram_bytes_read"] + k["dram_bytes_write"]) * (amps / float(1 << 30))
-        traffic_src = "profiles/r01_ncu_g4_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+        traffic_src = f"profiles/r01_ncu_g4_traffic.json [{key}] (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": pass_bytes,
-                "kernel": "4-qubit fused-gate pass: k_gate_pipe<4,...> (lowest target >= 3) / k_gate_tile<4,...> (lowest target <= 2)",
-                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-                "avg_launch_ms": dom_ms, "launches_timed": len(g4),
-                "share_of_step": float(np.sum(g4) / np.sum([p[2] for p in per_gate])) if g4 else None,
+                "kernel": dom, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                "avg_launch_ms": dom_ms, "launches_timed": kernels[dom]["launches"],
+                "share_of_step": kernels[dom]["share_of_step"], "kernels": kernels,
                 "per_gate_ms": [round(p[2], 4) for p in per_gate],
-                "per_gate_lowest_target": [p[1] for p in per_gate]}
+                "per_gate_lowest_target": [p[1][0] if p[1] else None for p in per_gate]}
 
     if rank == 0:
         cpu = None

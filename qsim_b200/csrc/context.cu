@@ -204,6 +204,7 @@ int qb200_ctx_set_tuning(qb200_ctx* ctx, const char* key, int value) {
   else if (!std::strcmp(key, "prefetch")) ctx->tune.prefetch = value;
   else if (!std::strcmp(key, "big")) ctx->tune.big = value;
   else if (!std::strcmp(key, "tc")) ctx->tune.tc = value;
+  else if (!std::strcmp(key, "tc_low")) ctx->tune.tc_low = value;
   else return QB200_ERR_INVALID;
   return QB200_OK;
 }

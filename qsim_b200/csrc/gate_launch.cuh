@@ -210,9 +210,11 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
 
   // fp32 G = 4, 5 gates: tcgen05 3xTF32 kernel (gate_tc.cuh); tiles of 128 groups
   if constexpr (sizeof(FP) == 4 && !EXPECT) {
-    // auto (-1): G = 5 only -- 3.5-3.7 ms against 5.95 ms on the CUDA cores at n = 30; the G = 4
-    // tensor-core pass (3.35 ms) still loses to the cp.async FFMA2 kernel (2.8-3.0 ms)
-    const bool use_tc = ctx->tune.tc > 0 || (ctx->tune.tc < 0 && nq == 5);
+    // auto (-1): every G = 5 pass (2.7 ms against 5.95 ms on the CUDA cores at n = 30) and the G = 4
+    // passes whose lowest target (the second lowest when bit 0 is a target) is >= tc_low: below
+    // that the per-thread row pieces are too scattered and the cp.async / warp-tile kernels win.
+    const unsigned low_t = nq >= 2 && qs[0] == 0 ? qs[1] : (nq >= 1 ? qs[0] : 0);
+    const bool use_tc = ctx->tune.tc > 0 || (ctx->tune.tc < 0 && (nq == 5 || (int) low_t >= ctx->tune.tc_low));
     if (!ctx->tune.force_generic && (nq == 4 || nq == 5) && aligned16 && use_tc && n >= nq + nc + 7) {
       Geom tg;
       int trc = make_geom(n, qs, nq, cqs, nc, cvals, false, &tg);

@@ -63,6 +63,9 @@ __device__ __forceinline__ void mma_commit(uint32_t mbar) {
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -409,41 +412,62 @@ k_gate_tc(float* __restrict__ st, const __grid_constant__ Geom g,
 // lane, the MMAs read A from TMEM (tcgen05.mma [d], [a], b-desc) and only W (a few KB) comes from
 // shared memory.  No generic->async proxy fence per tile, no operand traffic on the shared-memory
 // port, no operand buffers in shared memory (residency is bounded by TMEM columns alone).
-// TMEM columns of buffer b: [A_hi KF][A_lo KF][D KF].
+// TMEM columns of buffer b: MT x [A_hi KF][A_lo KF][D KF].
 // ---------------------------------------------------------------------------------------------
 template <int G, int NBUF>
 __host__ __device__ constexpr int tca_tmem_cols() {
   const int need = NBUF * 3 * TcShape<G>::KF;
   return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
 }
-template <int G>
-constexpr size_t tca_smem_bytes() { return 1024 + 2 * TcShape<G>::B_TILE; }
+// W_hi, W_lo, W_c (+ a RING-deep cp.async staging ring of raw tiles, 64 B (G=4) / 128 B (G=5) per thread and stage)
+template <int G, int RING, int MT>
+constexpr size_t tca_smem_bytes() {
+  return 1024 + 3 * TcShape<G>::B_TILE + (size_t) RING * kTcThreads * MT * (TcShape<G>::N / 2) * 8;
+}
 
-template <int G, bool PAIR, int NBUF, int PF, int MINB>
-__global__ void __launch_bounds__(kTcThreads, MINB)
+// Mean relative shrink of one pass caused by the tensor core's truncating fp32 accumulation,
+// measured as norm drift over 64 random passes (tools/tc_check.py): -1.7355e-7 (G = 4) and
+// -3.0130e-7 (G = 5) on the squared norm.  It is cancelled by a fourth, tiny MMA term
+// A_hi * (c W_hi) with c = half the drift.
+template <int G> __host__ __device__ constexpr float tc_bias() { return G == 4 ? 0.86777e-7f : 1.50648e-7f; }
+
+// MT = 128-row MMA tiles per CTA iteration (256 threads each): MT = 2 halves the barriers per byte for G = 4
+// COMP = add the accumulation-bias compensation term
+// RING = 0: register prefetch PF tiles ahead; RING >= 2: cp.async staging ring, RING - 1 tiles ahead
+// (cp.async groups are waited for exactly; LDG results share counting scoreboards, so a register
+// prefetch deeper than one tile does not buy latency)
+template <int G, bool PAIR, int NBUF, int PF, int MT, bool COMP, int RING, int MINB>
+__global__ void __launch_bounds__(kTcThreads * MT, MINB)
 k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
            const __grid_constant__ MatParam<float, G> mat) {
   using S = TcShape<G>;
   constexpr int N = S::N, KF = S::KF, HN = N / 2;
   constexpr int CHUNKS = HN / 2;
-  constexpr int TCOLS = tca_tmem_cols<G, NBUF>();
+  constexpr int TCOLS = tca_tmem_cols<G, NBUF * MT>();
+  constexpr int BUFC = MT * 3 * KF;  // TMEM columns of one buffer: MT x [A_hi | A_lo | D]
   static_assert(NBUF == 1 || NBUF == 2, "one or two operand/accumulator buffers");
-  static_assert(NBUF * 3 * KF <= 512, "tensor memory has 512 columns");
+  static_assert(NBUF * MT * 3 * KF <= 512, "tensor memory has 512 columns");
   extern __shared__ unsigned char tc_raw[];
   __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ __align__(8) uint64_t full_bar;  // all rows of the tile are in TMEM (count = threads)
   __shared__ uint32_t tmem_slot;
 
   const uint32_t t = threadIdx.x;
   const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  const uint32_t row = t & 127, half = t >> 7;
+  const uint32_t row = t & 127, half = (t >> 7) & 1, mt = MT == 1 ? 0 : t >> 8;
   const uint32_t raw_s = smem_u32(tc_raw);
   const uint32_t base_s = (raw_s + 1023u) & ~1023u;
   unsigned char* const base_p = tc_raw + (base_s - raw_s);
-  const uint32_t bhi_s = base_s, blo_s = base_s + S::B_TILE;
+  const uint32_t bhi_s = base_s, blo_s = base_s + S::B_TILE, bc_s = base_s + 2 * S::B_TILE;
   unsigned char* const bhi_p = base_p;
   unsigned char* const blo_p = base_p + S::B_TILE;
+  unsigned char* const bc_p = base_p + 2 * S::B_TILE;
+  // staging ring: stage s, 16-byte slot q, thread t at ((s * CHUNKS + q) * NT + t) * 16 (thread-private, conflict free)
+  constexpr int NT = kTcThreads * MT;
+  unsigned char* const ring_p = base_p + 3 * S::B_TILE + t * 16;
+  const uint32_t ring_s = base_s + 3 * S::B_TILE + t * 16;
 
-  for (uint32_t idx = t; idx < (uint32_t) (KF * KF); idx += kTcThreads) {
+  for (uint32_t idx = t; idx < (uint32_t) (KF * KF); idx += kTcThreads * MT) {
     const uint32_t n = idx / KF, k = idx % KF;
     const uint32_t r = n >> 1, c = k >> 1;
     const float ur = mat.m[2 * (r * N + c)], ui = mat.m[2 * (r * N + c) + 1];
@@ -452,6 +476,7 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
     const uint32_t off = (k >> 5) * S::B_ATOM + sw128_off(n, (k & 31) >> 2) + (k & 3) * 4;
     *reinterpret_cast<float*>(bhi_p + off) = hi;
     *reinterpret_cast<float*>(blo_p + off) = w - hi;
+    *reinterpret_cast<float*>(bc_p + off) = COMP ? tc_bias<G>() * hi : 0.f;
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
@@ -462,6 +487,7 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
   if (t == 0) {
     tc::mbar_init(smem_u32(&mbar[0]), 1);
     tc::mbar_init(smem_u32(&mbar[1]), 1);
+    tc::mbar_init(smem_u32(&full_bar), kTcThreads * MT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc::fence_async_smem();  // W was written through the generic proxy, the MMAs read it through the async proxy
@@ -470,16 +496,16 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
   tc::fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
   // this thread's lane (its row) and its half of the K / N columns inside a [KF]-wide block
-  const uint32_t tmem_mine = tmem_base + (((warp & 3) * 32u) << 16) + half * N;
+  const uint32_t tmem_mine = tmem_base + (((warp & 3) * 32u) << 16) + mt * 3 * KF + half * N;
   constexpr uint32_t idesc = tc::instr_desc_tf32(KF);
 
-  const uint64_t ntiles = g.work >> 7;
+  const uint64_t ntiles = g.work >> 7 >> (MT - 1);  // CTA tiles of 128 * MT groups
   const uint64_t stride = gridDim.x;
 
   const uint64_t thread_off = 8 * (expand_index(row, g) + (half ? g.xs[G - 1] : 0));
   unsigned char* const st_b = reinterpret_cast<unsigned char*>(st);
   auto tile_ptr = [&](uint64_t tile) {
-    uint64_t i = tile << 7;
+    uint64_t i = (tile * MT + mt) << 7;
     for (uint32_t k = 0; k < g.npos; ++k) {
       const uint64_t lo = i & ((uint64_t{1} << g.pos[k]) - 1);
       i = ((i - lo) << 1) | lo;
@@ -488,8 +514,7 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
   };
   auto eo = [&](int j) { return 8 * elem_offset<G>(j, g); };
 
-  auto load_mine = [&](uint64_t tile, uint4 (&x)[CHUNKS]) {
-    const unsigned char* const p = tile_ptr(tile);
+  auto load_mine = [&](const unsigned char* p, uint4 (&x)[CHUNKS]) {
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
       if constexpr (PAIR) {
@@ -500,6 +525,28 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
         x[c] = make_uint4(a.x, a.y, b.x, b.y);
       }
     }
+  };
+
+  auto ring_issue = [&](uint64_t tile, int stg) {
+    if (tile < ntiles) {
+      const unsigned char* const p = tile_ptr(tile);
+      const uint32_t dst = ring_s + (uint32_t) (stg * CHUNKS) * NT * 16;
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        if constexpr (PAIR) {
+          cp_async16(dst + c * NT * 16, p + eo(2 * c));
+        } else {
+          cp_async8(dst + c * NT * 16, p + eo(2 * c));
+          cp_async8(dst + c * NT * 16 + 8, p + eo(2 * c + 1));
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  auto ring_read = [&](int stg, uint4 (&x)[CHUNKS]) {
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+      x[c] = *reinterpret_cast<const uint4*>(ring_p + (size_t) (stg * CHUNKS + c) * NT * 16);
   };
 
   // hi/lo split in registers, written to this thread's TMEM lane: columns [A_hi | A_lo] of buffer b
@@ -516,24 +563,28 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
         l[4 * c + e] = __float_as_uint(xf - hf);
       }
     }
-    tc::tmem_st(tmem_mine + b * 3 * KF, h);
-    tc::tmem_st(tmem_mine + b * 3 * KF + KF, l);
+    tc::tmem_st(tmem_mine + b * BUFC, h);
+    tc::tmem_st(tmem_mine + b * BUFC + KF, l);
     tc::tmem_st_wait();
   };
 
   auto issue_mmas = [&](int b, uint32_t mb) {
     tc::fence_after();
-    const uint32_t ahi = tmem_base + b * 3 * KF, alo = ahi + KF, d = ahi + 2 * KF;
-    uint32_t acc = 0;
 #pragma unroll
-    for (int term = 0; term < 3; ++term) {
-      const uint32_t ab = term == 0 ? alo : ahi;
-      const uint32_t bb = term == 1 ? blo_s : bhi_s;
+    for (int m = 0; m < MT; ++m) {
+      const uint32_t ahi = tmem_base + b * BUFC + m * 3 * KF, alo = ahi + KF, d = ahi + 2 * KF;
+      uint32_t acc = 0;
+      // smallest terms first: A_hi (c W_hi), A_lo W_hi, A_hi W_lo, A_hi W_hi
 #pragma unroll
-      for (int k = 0; k < KF / 8; ++k) {
-        const uint64_t bd = tc::smem_desc_sw128(bb + (k >> 2) * S::B_ATOM + (k & 3) * 32);
-        tc::mma_tf32_ts(d, ab + 8 * k, bd, idesc, acc);
-        acc = 1;
+      for (int term = COMP ? 0 : 1; term < 4; ++term) {
+        const uint32_t ab = term == 1 ? alo : ahi;
+        const uint32_t bb = term == 0 ? bc_s : term == 2 ? blo_s : bhi_s;
+#pragma unroll
+        for (int k = 0; k < KF / 8; ++k) {
+          const uint64_t bd = tc::smem_desc_sw128(bb + (k >> 2) * S::B_ATOM + (k & 3) * 32);
+          tc::mma_tf32_ts(d, ab + 8 * k, bd, idesc, acc);
+          acc = 1;
+        }
       }
     }
     tc::mma_commit(mb);
@@ -544,8 +595,7 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
     tc::fence_after();
   };
 
-  auto store_mine = [&](uint64_t tile, const uint32_t (&v)[N]) {
-    unsigned char* const p = tile_ptr(tile);
+  auto store_mine = [&](unsigned char* p, const uint32_t (&v)[N]) {
 #pragma unroll
     for (int j = 0; j < HN; j += (PAIR ? 2 : 1)) {
       if constexpr (PAIR) {
@@ -557,53 +607,112 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
   };
 
   static_assert(PF == 1 || PF == 2, "prefetch one or two tiles ahead");
-  uint4 cur[CHUNKS], nxt[CHUNKS], nx2[PF == 2 ? CHUNKS : 1];
-  uint64_t tile = blockIdx.x, prev_tile = 0;
-  if (tile < ntiles) load_mine(tile, cur);
-  if constexpr (PF == 2) {
-    if (tile + stride < ntiles) load_mine(tile + stride, nxt);
-  }
-  uint32_t it = 0;
-  for (; tile < ntiles; tile += stride, ++it) {
-    const int b = it % NBUF;
-    uint32_t v[N];
-    if constexpr (NBUF == 1) {
-      if (it > 0) {
-        wait_tile(it - 1);
-        tc::tmem_ld(tmem_mine + 2 * KF, v);
+  if constexpr (RING >= 2) {
+    const uint64_t first = blockIdx.x;
+#pragma unroll
+    for (int sg = 0; sg < RING - 1; ++sg) ring_issue(first + sg * stride, sg);
+    int sg = 0;
+    uint32_t it = 0;
+    uint64_t prev_tile = 0;
+    for (uint64_t tile = first; tile < ntiles; tile += stride, ++it) {
+      const int b = it % NBUF;
+      uint32_t v[N];
+      if constexpr (NBUF == 1) {
+        if (it > 0) {
+          wait_tile(it - 1);
+          tc::tmem_ld(tmem_mine + 2 * KF, v);
+        }
       }
-    }
-    split_to_tmem(cur, b);
-    if constexpr (PF == 2) {
-      if (tile + 2 * stride < ntiles) load_mine(tile + 2 * stride, nx2);
-    } else {
-      if (tile + stride < ntiles) load_mine(tile + stride, nxt);
-    }
-    tc::fence_before();
-    __syncthreads();
-    if (warp == 0) {
-      if (tc::elect_one()) issue_mmas(b, smem_u32(&mbar[b]));
-      __syncwarp();
+      cp_async_wait<RING - 2>();  // this thread's pieces of tile `tile` (stage sg) have landed
+      uint4 x[CHUNKS];
+      ring_read(sg, x);
+      split_to_tmem(x, b);
+      // refill the stage read one iteration ago (by this same thread: no cross-thread hazard)
+      int sp = sg + RING - 1;
+      if (sp >= RING) sp -= RING;
+      ring_issue(tile + (RING - 1) * stride, sp);
+      // split barrier: everybody arrives, only the issuing warp waits -- the other warps go straight
+      // on to storing the previous tile instead of idling until the slowest warp has written its rows
+      tc::fence_before();
+      tc::mbar_arrive(smem_u32(&full_bar));
+      if (warp == 0) {
+        tc::mbar_wait(smem_u32(&full_bar), it & 1);
+        if (tc::elect_one()) issue_mmas(b, smem_u32(&mbar[b]));
+        __syncwarp();
+      }
+      if (it > 0) {
+        if constexpr (NBUF == 2) {
+          wait_tile(it - 1);
+          tc::tmem_ld(tmem_mine + ((it - 1) & 1) * BUFC + 2 * KF, v);
+        }
+        store_mine(tile_ptr(prev_tile), v);
+      }
+      prev_tile = tile;
+      if (++sg == RING) sg = 0;
     }
     if (it > 0) {
-      if constexpr (NBUF == 2) {
-        wait_tile(it - 1);
-        tc::tmem_ld(tmem_mine + ((it - 1) & 1) * 3 * KF + 2 * KF, v);
+      uint32_t v[N];
+      wait_tile(it - 1);
+      tc::tmem_ld(tmem_mine + ((it - 1) % NBUF) * BUFC + 2 * KF, v);
+      store_mine(tile_ptr(prev_tile), v);
+    }
+    cp_async_wait<0>();
+  } else {
+    // tile pointers are computed once per tile (when its loads are issued) and carried along
+    uint4 cur[CHUNKS], nxt[CHUNKS], nx2[PF == 2 ? CHUNKS : 1];
+    unsigned char *p_cur = nullptr, *p_nxt = nullptr, *p_nx2 = nullptr, *p_prev = nullptr;
+    uint64_t tile = blockIdx.x;
+    if (tile < ntiles) { p_cur = tile_ptr(tile); load_mine(p_cur, cur); }
+    if constexpr (PF == 2) {
+      if (tile + stride < ntiles) { p_nxt = tile_ptr(tile + stride); load_mine(p_nxt, nxt); }
+    }
+    uint32_t it = 0;
+    for (; tile < ntiles; tile += stride, ++it) {
+      const int b = it % NBUF;
+      uint32_t v[N];
+      if constexpr (NBUF == 1) {
+        if (it > 0) {
+          wait_tile(it - 1);
+          tc::tmem_ld(tmem_mine + 2 * KF, v);
+        }
       }
-      store_mine(prev_tile, v);
+      split_to_tmem(cur, b);
+      if constexpr (PF == 2) {
+        if (tile + 2 * stride < ntiles) { p_nx2 = tile_ptr(tile + 2 * stride); load_mine(p_nx2, nx2); }
+      } else {
+        if (tile + stride < ntiles) { p_nxt = tile_ptr(tile + stride); load_mine(p_nxt, nxt); }
+      }
+      // split barrier: everybody arrives, only the issuing warp waits -- the other warps go straight
+      // on to storing the previous tile instead of idling until the slowest warp has written its rows
+      tc::fence_before();
+      tc::mbar_arrive(smem_u32(&full_bar));
+      if (warp == 0) {
+        tc::mbar_wait(smem_u32(&full_bar), it & 1);
+        if (tc::elect_one()) issue_mmas(b, smem_u32(&mbar[b]));
+        __syncwarp();
+      }
+      if (it > 0) {
+        if constexpr (NBUF == 2) {
+          wait_tile(it - 1);
+          tc::tmem_ld(tmem_mine + ((it - 1) & 1) * BUFC + 2 * KF, v);
+        }
+        store_mine(p_prev, v);
+      }
+      p_prev = p_cur;
+      p_cur = p_nxt;
+      if constexpr (PF == 2) p_nxt = p_nx2;
+  #pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        cur[c] = nxt[c];
+        if constexpr (PF == 2) nxt[c] = nx2[c];
+      }
     }
-    prev_tile = tile;
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-      cur[c] = nxt[c];
-      if constexpr (PF == 2) nxt[c] = nx2[c];
+    if (it > 0) {
+      uint32_t v[N];
+      wait_tile(it - 1);
+      tc::tmem_ld(tmem_mine + ((it - 1) % NBUF) * BUFC + 2 * KF, v);
+      store_mine(p_prev, v);
     }
-  }
-  if (it > 0) {
-    uint32_t v[N];
-    wait_tile(it - 1);
-    tc::tmem_ld(tmem_mine + ((it - 1) % NBUF) * 3 * KF + 2 * KF, v);
-    store_mine(prev_tile, v);
   }
   tc::fence_before();
   __syncthreads();

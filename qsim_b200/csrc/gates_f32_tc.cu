@@ -38,13 +38,16 @@ int launch_tc_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
 }
 
 
-template <int G, bool PAIR, int NBUF, int PF, int MINB>
+template <int G, bool PAIR, int NBUF, int PF, int MT, bool COMP, int RING, int MINB>
 int launch_tca_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
-  auto kern = k_gate_tca<G, PAIR, NBUF, PF, MINB>;
-  constexpr size_t smem = tca_smem_bytes<G>();
+  auto kern = k_gate_tca<G, PAIR, NBUF, PF, MT, COMP, RING, MINB>;
+  constexpr size_t smem = tca_smem_bytes<G, RING, MT>();
   static const int occ = [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    int nb = 512 / tca_tmem_cols<G, NBUF>();  // tensor memory is the only residency limit
+    int nb = 512 / tca_tmem_cols<G, NBUF * MT>();  // tensor memory (and 2048 threads) bound the residency
+    if (nb * kTcThreads * MT > 2048) nb = 2048 / (kTcThreads * MT);
+    const int smem_limit = (int) ((227 * 1024) / (smem + 1024 + 64));
+    if (nb > smem_limit) nb = smem_limit;
     if (nb > MINB) nb = MINB;
     if (nb < 1) nb = 1;
     if (getenv("QB200_VERBOSE")) fprintf(stderr, "k_gate_tca<%d>: smem %zu, blocks per SM %d\n", G, smem, nb);
@@ -52,10 +55,10 @@ int launch_tca_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
   }();
   MatParam<float, G> mat;
   mat.fill(m);
-  const uint64_t tiles = g.work >> 7;
+  const uint64_t tiles = g.work >> 7 >> (MT - 1);
   const uint64_t persistent = uint64_t{kNumSMs} * occ;
   const uint32_t blocks = (uint32_t) (tiles < persistent ? tiles : persistent);
-  kern<<<blocks, kTcThreads, smem, ctx->stream>>>(st, g, mat);
+  kern<<<blocks, kTcThreads * MT, smem, ctx->stream>>>(st, g, mat);
   QB_LAUNCHED(ctx);
   return QB200_OK;
 }
@@ -64,13 +67,21 @@ int launch_tca_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
 
 int launch_tc_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool pair, const float* m) {
   const bool alt = ctx->tune.tc == 2;  // alternative shapes (tools/tc_check.py)
-  if (ctx->tune.tc == 3) {  // A operand in tensor memory, double-buffered
-    if (nq == 4) return pair ? launch_tca_shape<4, true, 2, 2, 2>(ctx, st, g, m) : launch_tca_shape<4, false, 2, 2, 2>(ctx, st, g, m);
-    if (nq == 5) return pair ? launch_tca_shape<5, true, 1, 1, 2>(ctx, st, g, m) : launch_tca_shape<5, false, 1, 1, 2>(ctx, st, g, m);
+  if (ctx->tune.tc < 0 || ctx->tune.tc == 3) {  // default: A operand in tensor memory, bias-compensated
+    if (nq == 4) return pair ? launch_tca_shape<4, true, 1, 2, 1, true, 0, 3>(ctx, st, g, m) : launch_tca_shape<4, false, 1, 2, 1, true, 0, 3>(ctx, st, g, m);
+    if (nq == 5) return pair ? launch_tca_shape<5, true, 1, 1, 1, true, 0, 2>(ctx, st, g, m) : launch_tca_shape<5, false, 1, 1, 1, true, 0, 2>(ctx, st, g, m);
   }
-  if (ctx->tune.tc == 4) {  // A operand in tensor memory, single-buffered, more CTAs
-    if (nq == 4) return pair ? launch_tca_shape<4, true, 1, 2, 4>(ctx, st, g, m) : launch_tca_shape<4, false, 1, 2, 4>(ctx, st, g, m);
-    if (nq == 5) return pair ? launch_tca_shape<5, true, 2, 1, 1>(ctx, st, g, m) : launch_tca_shape<5, false, 2, 1, 1>(ctx, st, g, m);
+  if (ctx->tune.tc == 4) {  // ... without the compensation term (plain 3xTF32)
+    if (nq == 4) return pair ? launch_tca_shape<4, true, 1, 2, 1, false, 0, 3>(ctx, st, g, m) : launch_tca_shape<4, false, 1, 2, 1, false, 0, 3>(ctx, st, g, m);
+    if (nq == 5) return pair ? launch_tca_shape<5, true, 1, 1, 1, false, 0, 2>(ctx, st, g, m) : launch_tca_shape<5, false, 1, 1, 1, false, 0, 2>(ctx, st, g, m);
+  }
+  if (ctx->tune.tc == 5) {  // ... cp.async staging ring, 3 tiles ahead, four CTAs per SM
+    if (nq == 4) return pair ? launch_tca_shape<4, true, 1, 1, 1, true, 3, 4>(ctx, st, g, m) : launch_tca_shape<4, false, 1, 1, 1, true, 3, 4>(ctx, st, g, m);
+    if (nq == 5) return pair ? launch_tca_shape<5, true, 1, 1, 1, true, 3, 2>(ctx, st, g, m) : launch_tca_shape<5, false, 1, 1, 1, true, 3, 2>(ctx, st, g, m);
+  }
+  if (ctx->tune.tc == 6) {  // ... ring of 4, three CTAs per SM
+    if (nq == 4) return pair ? launch_tca_shape<4, true, 1, 1, 1, true, 4, 3>(ctx, st, g, m) : launch_tca_shape<4, false, 1, 1, 1, true, 4, 3>(ctx, st, g, m);
+    if (nq == 5) return pair ? launch_tca_shape<5, true, 1, 1, 1, true, 2, 2>(ctx, st, g, m) : launch_tca_shape<5, false, 1, 1, 1, true, 2, 2>(ctx, st, g, m);
   }
   if (nq == 4) {
     if (alt) {
