@@ -721,4 +721,215 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_gate_tcx: the same tensor-memory data path, written for the cases k_gate_tca does not cover:
+// 6-qubit gates (K = N = 128: 384 TMEM columns, W tiles of 64 KB, one CTA per SM, the half row
+// processed in 32-float pieces to stay inside the register file) and EXPECTATION VALUES for
+// G = 4, 5, 6 (read-only: D = U x through the MMAs, then <x|D> per row in the epilogue with x
+// re-read from tensor memory as A_hi + A_lo, which is exact; products in fp32, accumulation in
+// double like lib/simulator_basic.h:323-324).  Matrix from device memory (a 6-qubit matrix does
+// not fit the kernel parameter space).  One operand/accumulator buffer, one tile of prefetch.
+// ---------------------------------------------------------------------------------------------
+template <int G>
+constexpr size_t tcx_smem_bytes() { return 1024 + 3 * TcShape<G>::B_TILE; }
+
+template <int G, bool PAIR, bool EXPECT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_gate_tcx(float* __restrict__ st, const __grid_constant__ Geom g, const float* __restrict__ umat,
+           const float comp, double* __restrict__ partials) {
+  using S = TcShape<G>;
+  constexpr int N = S::N, KF = S::KF, HN = N / 2;  // this thread: HN amplitudes = N floats
+  constexpr int CHUNKS = HN / 2;
+  constexpr int PIECE = N < 32 ? N : 32;           // floats per TMEM transfer
+  constexpr int NPIECE = N / PIECE;
+  constexpr int TCOLS = tca_tmem_cols<G, 1>();
+  extern __shared__ unsigned char tc_raw[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t t = threadIdx.x;
+  const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const uint32_t row = t & 127, half = t >> 7;
+  const uint32_t raw_s = smem_u32(tc_raw);
+  const uint32_t base_s = (raw_s + 1023u) & ~1023u;
+  unsigned char* const base_p = tc_raw + (base_s - raw_s);
+  const uint32_t bhi_s = base_s, blo_s = base_s + S::B_TILE, bc_s = base_s + 2 * S::B_TILE;
+
+  for (uint32_t idx = t; idx < (uint32_t) (KF * KF); idx += kTcThreads) {
+    const uint32_t n = idx / KF, k = idx % KF;
+    const uint32_t r = n >> 1, c = k >> 1;
+    const float ur = umat[2 * (r * N + c)], ui = umat[2 * (r * N + c) + 1];
+    const float w = (n & 1) ? ((k & 1) ? ur : ui) : ((k & 1) ? -ui : ur);
+    const float hi = tc::tf32_hi(w);
+    const uint32_t off = (k >> 5) * S::B_ATOM + sw128_off(n, (k & 31) >> 2) + (k & 3) * 4;
+    *reinterpret_cast<float*>(base_p + off) = hi;
+    *reinterpret_cast<float*>(base_p + S::B_TILE + off) = w - hi;
+    *reinterpret_cast<float*>(base_p + 2 * S::B_TILE + off) = comp * hi;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "n"(TCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (t == 0) {
+    tc::mbar_init(smem_u32(&mbar), 1);
+    tc::mbar_init(smem_u32(&full_bar), kTcThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc::fence_async_smem();
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
+  // TMEM columns: [A_hi KF][A_lo KF][D KF]; this thread: its lane, its half of each block
+  const uint32_t tmem_mine = tmem_base + (((warp & 3) * 32u) << 16) + half * N;
+  constexpr uint32_t idesc = tc::instr_desc_tf32(KF);
+
+  const uint64_t ntiles = g.work >> 7;
+  const uint64_t stride = gridDim.x;
+  const uint64_t thread_off = 8 * (expand_index(row, g) + (half ? g.xs[G - 1] : 0));
+  unsigned char* const st_b = reinterpret_cast<unsigned char*>(st);
+  auto tile_ptr = [&](uint64_t tile) {
+    uint64_t i = tile << 7;
+    for (uint32_t k = 0; k < g.npos; ++k) {
+      const uint64_t lo = i & ((uint64_t{1} << g.pos[k]) - 1);
+      i = ((i - lo) << 1) | lo;
+    }
+    return st_b + 8 * i + thread_off;
+  };
+  auto eo = [&](int j) { return 8 * elem_offset<G>(j, g); };
+
+  auto load_mine = [&](const unsigned char* p, uint4 (&x)[CHUNKS]) {
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      if constexpr (PAIR) {
+        x[c] = *reinterpret_cast<const uint4*>(p + eo(2 * c));
+      } else {
+        const uint2 a = *reinterpret_cast<const uint2*>(p + eo(2 * c));
+        const uint2 b = *reinterpret_cast<const uint2*>(p + eo(2 * c + 1));
+        x[c] = make_uint4(a.x, a.y, b.x, b.y);
+      }
+    }
+  };
+
+  auto split_to_tmem = [&](const uint4 (&x)[CHUNKS]) {
+#pragma unroll
+    for (int pc = 0; pc < NPIECE; ++pc) {
+      uint32_t h[PIECE], l[PIECE];
+#pragma unroll
+      for (int c = 0; c < PIECE / 4; ++c) {
+        const uint4 xv = x[pc * (PIECE / 4) + c];
+        const uint32_t w[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xf = __uint_as_float(w[e]);
+          const float hf = tc::tf32_hi(xf);
+          h[4 * c + e] = __float_as_uint(hf);
+          l[4 * c + e] = __float_as_uint(xf - hf);
+        }
+      }
+      tc::tmem_st(tmem_mine + pc * PIECE, h);
+      tc::tmem_st(tmem_mine + KF + pc * PIECE, l);
+    }
+    tc::tmem_st_wait();
+  };
+
+  auto issue_mmas = [&]() {
+    tc::fence_after();
+    const uint32_t ahi = tmem_base, alo = ahi + KF, d = ahi + 2 * KF;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int term = EXPECT ? 1 : 0; term < 4; ++term) {
+      const uint32_t ab = term == 1 ? alo : ahi;
+      const uint32_t bb = term == 0 ? bc_s : term == 2 ? blo_s : bhi_s;
+#pragma unroll 4
+      for (int k = 0; k < KF / 8; ++k) {
+        const uint64_t bd = tc::smem_desc_sw128(bb + (k >> 2) * S::B_ATOM + (k & 3) * 32);
+        tc::mma_tf32_ts(d, ab + 8 * k, bd, idesc, acc);
+        acc = 1;
+      }
+    }
+    tc::mma_commit(smem_u32(&mbar));
+  };
+
+  double ere = 0, eim = 0;
+  // tile it-1 is complete in TMEM: write it back (gate) or fold <x|D> into the accumulators (expectation)
+  auto epilogue = [&](unsigned char* p) {
+#pragma unroll
+    for (int pc = 0; pc < NPIECE; ++pc) {
+      uint32_t v[PIECE];
+      tc::tmem_ld(tmem_mine + 2 * KF + pc * PIECE, v);
+      if constexpr (EXPECT) {
+        uint32_t xh[PIECE], xl[PIECE];
+        tc::tmem_ld(tmem_mine + pc * PIECE, xh);
+        tc::tmem_ld(tmem_mine + KF + pc * PIECE, xl);
+#pragma unroll
+        for (int j = 0; j < PIECE / 2; ++j) {
+          const float xr = __uint_as_float(xh[2 * j]) + __uint_as_float(xl[2 * j]);
+          const float xi = __uint_as_float(xh[2 * j + 1]) + __uint_as_float(xl[2 * j + 1]);
+          const float re = __uint_as_float(v[2 * j]), im = __uint_as_float(v[2 * j + 1]);
+          ere += xr * re + xi * im;
+          eim += xr * im - xi * re;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < PIECE / 2; j += (PAIR ? 2 : 1)) {
+          const int a = pc * (PIECE / 2) + j;  // amplitude within the half row
+          if constexpr (PAIR) {
+            *reinterpret_cast<uint4*>(p + eo(a)) = make_uint4(v[2 * j], v[2 * j + 1], v[2 * j + 2], v[2 * j + 3]);
+          } else {
+            *reinterpret_cast<uint2*>(p + eo(a)) = make_uint2(v[2 * j], v[2 * j + 1]);
+          }
+        }
+      }
+    }
+  };
+
+  uint4 cur[CHUNKS], nxt[CHUNKS];
+  unsigned char *p_cur = nullptr, *p_nxt = nullptr, *p_prev = nullptr;
+  uint64_t tile = blockIdx.x;
+  if (tile < ntiles) { p_cur = tile_ptr(tile); load_mine(p_cur, cur); }
+  uint32_t it = 0;
+  for (; tile < ntiles; tile += stride, ++it) {
+    if (it > 0) {
+      tc::mbar_wait(smem_u32(&mbar), (it - 1) & 1);
+      tc::fence_after();
+      epilogue(p_prev);
+    }
+    split_to_tmem(cur);
+    if (tile + stride < ntiles) { p_nxt = tile_ptr(tile + stride); load_mine(p_nxt, nxt); }
+    tc::fence_before();
+    tc::mbar_arrive(smem_u32(&full_bar));
+    if (warp == 0) {
+      tc::mbar_wait(smem_u32(&full_bar), it & 1);
+      if (tc::elect_one()) issue_mmas();
+      __syncwarp();
+    }
+    p_prev = p_cur;
+    p_cur = p_nxt;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) cur[c] = nxt[c];
+  }
+  if (it > 0) {
+    tc::mbar_wait(smem_u32(&mbar), (it - 1) & 1);
+    tc::fence_after();
+    epilogue(p_prev);
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS) : "memory");
+  }
+  if constexpr (EXPECT) {
+    block_sum2<kTcThreads>(ere, eim);
+    if (t == 0) {
+      partials[2 * blockIdx.x] = ere;
+      partials[2 * blockIdx.x + 1] = eim;
+    }
+  }
+}
+
 }  // namespace qb200
