@@ -205,6 +205,8 @@ int qb200_ctx_set_tuning(qb200_ctx* ctx, const char* key, int value) {
   else if (!std::strcmp(key, "big")) ctx->tune.big = value;
   else if (!std::strcmp(key, "tc")) ctx->tune.tc = value;
   else if (!std::strcmp(key, "tc_low")) ctx->tune.tc_low = value;
+  else if (!std::strcmp(key, "tcx")) ctx->tune.tcx = value;
+  else if (!std::strcmp(key, "tc_comp6")) ctx->tune.tc_comp6 = value;
   else return QB200_ERR_INVALID;
   return QB200_OK;
 }

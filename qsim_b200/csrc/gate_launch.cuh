@@ -19,6 +19,9 @@ int launch_big_f32(qb200_ctx* ctx, float* st, const TileGeom& t, unsigned nq, co
 
 // fp32 G = 4, 5 gate passes on the tensor cores (gate_tc.cuh, instantiated in gates_f32_tc.cu)
 int launch_tc_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool pair, const float* m);
+// fp32 G = 6 gates and G = 4, 5, 6 expectation values on the tensor cores (k_gate_tcx)
+int launch_tcx_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool pair, const float* m,
+                   bool expect, double* out);
 
 template <typename FP> struct RegLimits;
 template <> struct RegLimits<float>  { static constexpr int kMaxG = 5; static constexpr int kMaxUnrollG = 4; };
@@ -235,6 +238,19 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
                       : launch_tile<4, false, 256, 3, 2>(ctx, st, t, m);
       }
       if (trc != QB200_ERR_UNSUPPORTED) return trc;
+    }
+  }
+
+  // fp32 G = 6 gates and G = 4, 5, 6 expectation values: tensor cores too (k_gate_tcx); tuning tcx = 0 keeps
+  // them on the FFMA2 kernels below
+  if constexpr (sizeof(FP) == 4) {
+    const bool want = EXPECT ? (nq >= 4 && nq <= 6) : nq == 6;
+    if (!ctx->tune.force_generic && want && aligned16 && ctx->tune.tc != 0 && ctx->tune.tcx != 0 && nc == 0 &&
+        n >= nq + 7) {
+      Geom tg;
+      int trc = make_geom(n, qs, nq, cqs, nc, cvals, false, &tg);
+      if (trc) return trc;
+      return launch_tcx_f32(ctx, st, tg, nq, qs[0] == 0, m, EXPECT, out);
     }
   }
 

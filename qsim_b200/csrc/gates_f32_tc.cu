@@ -63,7 +63,64 @@ int launch_tca_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
   return QB200_OK;
 }
 
+
+// G = 6 gates and tensor-core expectation values (k_gate_tcx): one CTA per SM, matrix from the
+// pinned->device staging ring
+template <int G, bool PAIR, bool EXPECT>
+int launch_tcx_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m, double* out) {
+  auto kern = k_gate_tcx<G, PAIR, EXPECT>;
+  constexpr size_t smem = tcx_smem_bytes<G>();
+  // resident CTAs per SM: TMEM columns (the allocation is the next power of two of 3 * KF), shared
+  // memory and registers (the runtime's occupancy query answers 1 for kernels that allocate TMEM)
+  static const int occ = [&] {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    int nb = 512 / tca_tmem_cols<G, 1>();
+    const int smem_limit = (int) ((227 * 1024) / (smem + 1024 + 64));
+    if (nb > smem_limit) nb = smem_limit;
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.numRegs > 0) {
+      const int reg_limit = 65536 / (((fa.numRegs + 7) / 8 * 8) * kTcThreads);
+      if (nb > reg_limit) nb = reg_limit;
+    }
+    if (nb < 1) nb = 1;
+    if (getenv("QB200_VERBOSE")) fprintf(stderr, "k_gate_tcx<%d,%d>: smem %zu, blocks per SM %d\n", G, (int) EXPECT, smem, nb);
+    return nb;
+  }();
+  const uint64_t tiles = g.work >> 7;
+  uint64_t persistent = uint64_t{kNumSMs} * occ;
+  if (EXPECT && persistent > kExpectMaxBlocks) persistent = kExpectMaxBlocks;
+  const uint32_t blocks = (uint32_t) (tiles < persistent ? tiles : persistent);
+  double* partials = nullptr;
+  if constexpr (EXPECT) {
+    int rc = ensure_scratch(ctx, (2 * size_t{blocks} + 2) * sizeof(double));
+    if (rc) return rc;
+    partials = (double*) ctx->scratch;
+  }
+  const void* dmat = nullptr;
+  int rc = stage_matrix(ctx, m, sizeof(float) * (size_t{2} << (2 * G)), &dmat);
+  if (rc) return rc;
+  // accumulation-bias compensation (see tc_bias): measured per G; none for expectation values
+  const float comp = EXPECT ? 0.f : (G == 4 ? tc_bias<4>() : G == 5 ? tc_bias<5>() : (float) ctx->tune.tc_comp6 * 1e-9f);
+  kern<<<blocks, kTcThreads, smem, ctx->stream>>>(st, g, (const float*) dmat, comp, partials);
+  QB_LAUNCHED(ctx);
+  stage_matrix_done(ctx);
+  if constexpr (EXPECT) return finish_expectation(ctx, partials, blocks, out);
+  return QB200_OK;
+}
+
 }  // namespace
+
+int launch_tcx_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool pair, const float* m,
+                   bool expect, double* out) {
+  if (expect) {
+    if (nq == 4) return pair ? launch_tcx_shape<4, true, true>(ctx, st, g, m, out) : launch_tcx_shape<4, false, true>(ctx, st, g, m, out);
+    if (nq == 5) return pair ? launch_tcx_shape<5, true, true>(ctx, st, g, m, out) : launch_tcx_shape<5, false, true>(ctx, st, g, m, out);
+    if (nq == 6) return pair ? launch_tcx_shape<6, true, true>(ctx, st, g, m, out) : launch_tcx_shape<6, false, true>(ctx, st, g, m, out);
+  } else if (nq == 6) {
+    return pair ? launch_tcx_shape<6, true, false>(ctx, st, g, m, out) : launch_tcx_shape<6, false, false>(ctx, st, g, m, out);
+  }
+  return QB200_ERR_UNSUPPORTED;
+}
 
 int launch_tc_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool pair, const float* m) {
   const bool alt = ctx->tune.tc == 2;  // alternative shapes (tools/tc_check.py)

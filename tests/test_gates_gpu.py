@@ -217,7 +217,8 @@ def test_big_kernel_every_layout(oracle, g):
     ExpectationValue; both launch shapes."""
     import qsim_b200
     ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
-    sim.set_tuning("tc", 0)  # 5-qubit gates default to the tensor-core kernel; this test is about k_gate_big
+    sim.set_tuning("tc", 0)  # 5/6-qubit gates and expectations default to the tensor-core kernels;
+    sim.set_tuning("tcx", 0)  # this test is about k_gate_big
     n = 12
     host = random_state(n, np.complex64, seed=g)
     st = ss.Create(n)
@@ -311,3 +312,51 @@ def test_tensor_core_kernel_large_state_round_trip(variant, drift):
         sim.ApplyGate(q, np.ascontiguousarray(u.conj().T), st)
     amp = 2.0 ** (-n / 2)
     assert np.abs(ss.to_numpy(st) - amp).max() < 1e-5 * amp * 100
+
+
+def test_tensor_core_6_qubit_gates_and_expectations(oracle):
+    """k_gate_tcx (gate_tc.cuh): 6-qubit gates and 4/5/6-qubit expectation values on the tensor cores.
+    Every third choice of 6 targets out of 13 qubits for the gate (572 layouts), every fifth choice of
+    4 / 5 / 6 targets for the expectation value, all against the oracle; the FFMA2 kernels (tuning
+    tcx = 0) must agree too."""
+    import qsim_b200
+    ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
+    n = 13
+    host = random_state(n, np.complex64, seed=66)
+    st = ss.Create(n)
+    for k, qs in enumerate(itertools.combinations(range(n), 6)):
+        if k % 3:
+            continue
+        m = random_matrix(6, seed=k % 7, cdtype=np.complex64)
+        ss.from_numpy(host, st)
+        sim.ApplyGate(list(qs), m, st)
+        err = np.abs(ss.to_numpy(st) - oracle.apply_gate(host.copy(), list(qs), m)).max()
+        assert err <= 4e-6, (qs, err)
+    ss.from_numpy(host, st)
+    for g in (4, 5, 6):
+        for k, qs in enumerate(itertools.combinations(range(n), g)):
+            if k % 5:
+                continue
+            m = random_matrix(g, seed=k % 11, cdtype=np.complex64)
+            want = oracle.expectation_value(host, list(qs), m)
+            sim.set_tuning("tcx", -1)
+            got = sim.ExpectationValue(list(qs), m, st)
+            assert abs(got - want) <= 2e-6 * (1 << g), (qs, got, want)
+            if k % 50 == 0:
+                sim.set_tuning("tcx", 0)
+                assert abs(sim.ExpectationValue(list(qs), m, st) - want) <= 2e-6 * (1 << g), qs
+    assert np.array_equal(ss.to_numpy(st), host)  # expectation values are read-only
+
+
+def test_tensor_core_6_qubit_gate_norm_drift():
+    """the compensation constant of the 6-qubit tensor-core gate: 16 random unitaries at n = 24 keep the norm"""
+    import qsim_b200
+    ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
+    n = 24
+    st = ss.Create(n)
+    ss.SetStateUniform(st)
+    rng = np.random.default_rng(9)
+    for i in range(16):
+        qs = sorted(rng.choice(np.arange(3, n), 6, replace=False).tolist())
+        sim.ApplyGate(qs, random_unitary(6, i, np.complex64), st)
+    assert abs(ss.Norm(st) - 1.0) < 16 * 1e-7
