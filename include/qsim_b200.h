@@ -70,7 +70,19 @@ int qb200_last_cuda_error(const qb200_ctx* ctx);
 const char* qb200_last_cuda_error_string(const qb200_ctx* ctx);
 /* Number of kernels this context has launched (bench.py's gpu_launches). */
 uint64_t qb200_launch_count(const qb200_ctx* ctx);
-/* Kernel-selection overrides for experiments: key/value pairs, see DESIGN.md. */
+/* Kernel-selection overrides for experiments and for the cross-check tests (defaults = -1 = auto):
+ *   gate_mode 0      one amplitude per access in the register kernels
+ *   force_generic 1  runtime-generic kernel for everything
+ *   tile 0/1/2       fp32 G=4 FFMA2 path: register kernels only / cp.async ring only / warp tile wherever legal
+ *   prefetch 0       no software-pipelined persistent loop in the register kernels
+ *   big 0/1          fp32 G=5,6 FFMA2 path: register+generic kernels / alternative launch shape
+ *   tc 0..6          fp32 G=4,5 gates on the tensor cores: 0 off; 1,2 operands staged in shared memory;
+ *                    3 = default data path (A operand in TMEM) forced for every layout; 4 without the
+ *                    accumulation-bias compensation term; 5,6 with a cp.async staging ring
+ *   tc_low k         auto policy: G=4 uses the tensor cores when its lowest non-zero target >= k (default 4)
+ *   tcx 0            keep G=6 gates and G=4..6 expectation values on the FFMA2 kernels
+ *   tc_comp6 v       compensation constant of the G=6 tensor-core gate in units of 1e-9 (default 276)
+ * Unknown keys return QB200_ERR_INVALID.  See DESIGN.md section 3. */
 int qb200_ctx_set_tuning(qb200_ctx* ctx, const char* key, int value);
 /* Event timing on the context's stream (CUDA events). */
 int qb200_timer_start(qb200_ctx* ctx);
