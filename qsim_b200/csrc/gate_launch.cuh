@@ -192,6 +192,12 @@ int launch_reg_mode(qb200_ctx* ctx, int mode, FP* st, const Geom& g, const FP* m
   return launch_reg<FP, G, kV1, EXPECT>(ctx, st, g, m, out);
 }
 
+}  // namespace qb200
+
+#include "gate_dbig.cuh"
+
+namespace qb200 {
+
 // One fused-gate pass: gate (EXPECT=false, in place) or expectation value.
 template <typename FP, bool EXPECT>
 int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned nq,
@@ -251,6 +257,19 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
       int trc = make_geom(n, qs, nq, cqs, nc, cvals, false, &tg);
       if (trc) return trc;
       return launch_tcx_f32(ctx, st, tg, nq, qs[0] == 0, m, EXPECT, out);
+    }
+  }
+
+  // fp64 G = 5, 6 gates and G = 4, 5, 6 expectation values: row-blocked DFMA kernel (gate_dbig.cuh)
+  if constexpr (sizeof(FP) == 8) {
+    const bool want = EXPECT ? (nq >= 4 && nq <= 6) : (nq == 5 || nq == 6);
+    if (!ctx->tune.force_generic && want && ctx->tune.big != 0) {
+      Geom dg;
+      int drc = make_geom(n, qs, nq, cqs, nc, cvals, false, &dg);
+      if (drc) return drc;
+      if (nq == 4) { if constexpr (EXPECT) return launch_dbig<4, true>(ctx, st, dg, m, out); }
+      if (nq == 5) return launch_dbig<5, EXPECT>(ctx, st, dg, m, out);
+      if (nq == 6) return launch_dbig<6, EXPECT>(ctx, st, dg, m, out);
     }
   }
 

@@ -23,12 +23,17 @@ ap.add_argument("--n", type=int, default=26)
 ap.add_argument("--depth", type=int, default=20)
 ap.add_argument("--fused", type=int, default=4)
 ap.add_argument("--p", type=float, default=0.001)
+ap.add_argument("--procs-per-gpu", type=int, default=1,
+                help="worker processes per GPU (time-sliced: fills the host-side gaps between a trajectory's launches)")
 args = ap.parse_args()
 
 with tempfile.NamedTemporaryFile("w", suffix=f"_rqc_q{args.n}", delete=False) as f:
     f.write(generate(args.n, args.depth, args.n))
     path = f.name
-res = run_farm(path, 0, args.num * args.gpus, gpus=args.gpus, p=args.p, max_fused_size=args.fused)
+ppg = args.procs_per_gpu
+res = run_farm(path, 0, args.num * args.gpus, gpus=args.gpus * ppg, p=args.p, max_fused_size=args.fused,
+               device_ids=[d for d in range(args.gpus) for _ in range(ppg)])
+res["procs_per_gpu"] = ppg
 os.unlink(path)
 res.pop("sums")
 res["mean"] = res["mean"][:8]
