@@ -386,7 +386,8 @@ def main():
         if g == 5:
             return "k_gate_big<5> (FFMA2)" if tc_off else "k_gate_tca<5> (tcgen05 3xTF32, A in TMEM)"
         if g == 4:
-            if not tc_off and low_t >= 4:
+            on_tc = qs[0] >= 4 or qs[0] == 2 or (qs[0] == 3 and qs[1] > 4) or (qs[0] == 0 and not (qs[1] == 1 and qs[2] == 2))
+            if not tc_off and on_tc:  # the dispatcher's per-layout rule (gate_launch.cuh)
                 return "k_gate_tca<4> (tcgen05 3xTF32, A in TMEM)"
             return "k_gate_tile<4> (FFMA2, warp tile)" if qs[0] <= 2 else "k_gate_pipe<4> (FFMA2, cp.async ring)"
         return f"k_gate_reg<{g}> (FFMA2)" if g < 6 else "k_gate_big<6> (FFMA2)"

@@ -79,7 +79,7 @@ uint64_t qb200_launch_count(const qb200_ctx* ctx);
  *   tc 0..6          fp32 G=4,5 gates on the tensor cores: 0 off; 1,2 operands staged in shared memory;
  *                    3 = default data path (A operand in TMEM) forced for every layout; 4 without the
  *                    accumulation-bias compensation term; 5,6 with a cp.async staging ring
- *   tc_low k         auto policy: G=4 uses the tensor cores when its lowest non-zero target >= k (default 4)
+ *   tc_low k         replace the per-layout G=4 tensor-core rule by: lowest non-zero target >= k
  *   tcx 0            keep G=6 gates and G=4..6 expectation values on the FFMA2 kernels
  *   tc_comp6 v       compensation constant of the G=6 tensor-core gate in units of 1e-9 (default 276)
  * Unknown keys return QB200_ERR_INVALID.  See DESIGN.md section 3. */

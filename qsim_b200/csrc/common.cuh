@@ -37,7 +37,7 @@ struct Tuning {
   int tc = -1;             // fp32 G=4,5 on the tensor cores (tcgen05 3xTF32): -1 auto, 0 off, 1..5 variants
   int tcx = -1;            // fp32 G=6 gates and G=4..6 expectation values on the tensor cores: 0 off
   int tc_comp6 = 276;      // accumulation-bias compensation of the G=6 tensor-core gate, in units of 1e-9
-  int tc_low = 4;          // auto: G=4 goes to the tensor cores when its lowest non-zero target >= tc_low
+  int tc_low = -1;         // -1: per-layout rule (gate_launch.cuh); k >= 0: G=4 on the tensor cores iff lowest non-zero target >= k
   int big = -1;            // -1 auto (on); 0 = fp32 G>=5 through the register/generic kernels;
                            // 1/2/3 = alternative launch shapes of k_gate_big (tools/microbench.py)
 };

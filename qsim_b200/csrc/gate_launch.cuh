@@ -220,10 +220,20 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
   // fp32 G = 4, 5 gates: tcgen05 3xTF32 kernel (gate_tc.cuh); tiles of 128 groups
   if constexpr (sizeof(FP) == 4 && !EXPECT) {
     // auto (-1): every G = 5 pass (2.7 ms against 5.95 ms on the CUDA cores at n = 30) and the G = 4
-    // passes whose lowest target (the second lowest when bit 0 is a target) is >= tc_low: below
-    // that the per-thread row pieces are too scattered and the cp.async / warp-tile kernels win.
-    const unsigned low_t = nq >= 2 && qs[0] == 0 ? qs[1] : (nq >= 1 ? qs[0] : 0);
-    const bool use_tc = ctx->tune.tc > 0 || (ctx->tune.tc < 0 && (nq == 5 || (int) low_t >= ctx->tune.tc_low));
+    // passes whose per-thread row pieces form runs of >= 32 contiguous bytes across neighbouring lanes;
+    // measured per layout (profiles/r01_tc_check.txt): lowest target >= 4, or 2, or 3 with the next
+    // one above bit 4, or bit 0 together with anything but {1, 2}.  The rest ([0,1,2,..], lowest
+    // target 1, [3,4,..]) is faster on the warp-tile / cp.async FFMA2 kernels.  tc_low >= 0 replaces
+    // the rule by a plain threshold on the lowest non-zero target (experiments).
+    bool g4_tc = false;
+    if (nq == 4) {
+      if (ctx->tune.tc_low >= 0) {
+        g4_tc = (int) (qs[0] == 0 ? qs[1] : qs[0]) >= ctx->tune.tc_low;
+      } else {
+        g4_tc = qs[0] >= 4 || qs[0] == 2 || (qs[0] == 3 && qs[1] > 4) || (qs[0] == 0 && !(qs[1] == 1 && qs[2] == 2));
+      }
+    }
+    const bool use_tc = ctx->tune.tc > 0 || (ctx->tune.tc < 0 && (nq == 5 || g4_tc));
     if (!ctx->tune.force_generic && (nq == 4 || nq == 5) && aligned16 && use_tc && n >= nq + nc + 7) {
       Geom tg;
       int trc = make_geom(n, qs, nq, cqs, nc, cvals, false, &tg);
