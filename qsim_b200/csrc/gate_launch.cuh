@@ -25,7 +25,7 @@ int launch_tcx_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool p
 
 template <typename FP> struct RegLimits;
 template <> struct RegLimits<float>  { static constexpr int kMaxG = 5; static constexpr int kMaxUnrollG = 4; };
-template <> struct RegLimits<double> { static constexpr int kMaxG = 4; static constexpr int kMaxUnrollG = 3; };
+template <> struct RegLimits<double> { static constexpr int kMaxG = 5; static constexpr int kMaxUnrollG = 5; };
 
 // Launch shape per (precision, G): the unrolled G>=4 (fp32) / G>=3 (fp64)
 // kernels want ~160 registers (data + one 64-bit address per group element),
@@ -34,6 +34,7 @@ template <typename FP, int G> constexpr int block_threads() {
   return (sizeof(FP) == 4 ? G <= 3 : G <= 2) ? 256 : 128;
 }
 template <typename FP, int G> constexpr int min_blocks() {
+  if (sizeof(FP) == 8 && G >= 5) return 1;  // 2^5 complex doubles = 128 registers of data alone
   return (sizeof(FP) == 4 ? G <= 3 : G <= 2) ? 2 : 3;
 }
 
@@ -99,7 +100,10 @@ template <typename FP, int G, int MODE, bool EXPECT>
 int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) {
   constexpr int NT = block_threads<FP, G>();
   constexpr int MINB = min_blocks<FP, G>();
-  constexpr bool UNROLL = G <= RegLimits<FP>::kMaxUnrollG;
+  // fp64: rows are unrolled (matrix elements become constant-bank operands of the DFMAs) where that
+  // measured faster at n = 29: G <= 3, G = 5 gates (11 ms against 16.5 ms through k_gate_dbig) and G = 4
+  // expectation values (5.1 ms against 8.0 ms); the G = 4 gate keeps the rolled row loop (5.0 ms against 7.2 ms)
+  constexpr bool UNROLL = sizeof(FP) == 8 ? (G <= 3 || G == 5 || EXPECT) : G <= RegLimits<FP>::kMaxUnrollG;
   using Mat = MatParam<FP, G>;
   Mat mat;
   mat.fill(m);
@@ -272,8 +276,10 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
 
   // fp64 G = 5, 6 gates and G = 4, 5, 6 expectation values: row-blocked DFMA kernel (gate_dbig.cuh)
   if constexpr (sizeof(FP) == 8) {
-    const bool want = EXPECT ? (nq >= 4 && nq <= 6) : (nq == 5 || nq == 6);
-    if (!ctx->tune.force_generic && want && ctx->tune.big != 0) {
+    // G = 6 always; G = 4, 5 only with tuning big = 2 (default: fully unrolled register kernels whose matrix
+    // elements are constant-bank operands of the DFMAs -- no load per MAC)
+    const bool want = nq == 6 || (EXPECT && nq == 5) || (ctx->tune.big == 2 && (EXPECT ? nq >= 4 : nq == 5));
+    if (!ctx->tune.force_generic && want && nq <= 6 && ctx->tune.big != 0) {
       Geom dg;
       int drc = make_geom(n, qs, nq, cqs, nc, cvals, false, &dg);
       if (drc) return drc;
