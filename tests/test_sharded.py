@@ -57,6 +57,51 @@ class OracleEngine:
         return self._stage[:count]
 
 
+class PeerOracleEngine(OracleEngine):
+    """Emulates the NVLink peer-memory engine (B200Engine(p2p=True)) over gloo: the same in-place
+    semantics as csrc/p2p_swap.cu -- the k local bits `local_bits` are swapped with k rank bits, for
+    every peer value b != my the amplitudes whose local bits equal b trade places with the peer's
+    amplitudes whose local bits equal my.  Exercises ShardedSimulator._swap_p2p on CPU."""
+    p2p = True
+    element_size = 4
+
+    class _Event:
+        def elapsed_time(self, other):
+            return 0.0
+
+    def __init__(self, n_local, dist):
+        super().__init__(n_local)
+        self.dist = dist
+
+    def event(self):
+        return self._Event()
+
+    def stream_barrier(self, dist):
+        dist.barrier()
+
+    def swap_global_local(self, peer_ranks, k, local_bits, my_value):
+        import torch
+        assert list(local_bits) == sorted(local_bits) and len(local_bits) == k
+        idx = np.arange(1 << self.n_local, dtype=np.int64)
+        val = np.zeros_like(idx)
+        for j, lb in enumerate(local_bits):
+            val |= ((idx >> lb) & 1) << j
+        reqs, incoming = [], {}
+        for b in range(1 << k):
+            if b == my_value:
+                continue
+            sel = np.nonzero(val == b)[0]
+            out = torch.from_numpy(np.ascontiguousarray(self.np[sel]).view(np.float32).copy())
+            inc = torch.empty_like(out)
+            incoming[b] = (sel, inc)
+            reqs.append(self.dist.isend(out, dst=peer_ranks[b]))
+            reqs.append(self.dist.irecv(inc, src=peer_ranks[b]))
+        for r in reqs:
+            r.wait()
+        for b, (sel, inc) in incoming.items():
+            self.np[sel] = inc.numpy().view(np.complex64)
+
+
 def random_ops(n, count, seed, max_local):
     rs = np.random.RandomState(seed)
     ops = []
@@ -87,14 +132,14 @@ def oracle_full(n, ops):
     return st
 
 
-def _worker(rank, world, port, n, ops, transfer_scalars, out_dir):
+def _worker(rank, world, port, n, ops, transfer_scalars, out_dir, p2p=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         g = world.bit_length() - 1
-        eng = OracleEngine(n - g)
+        eng = PeerOracleEngine(n - g, dist) if p2p else OracleEngine(n - g)
         sim = ShardedSimulator(n, eng, dist=dist, rank=rank, world_size=world, transfer_scalars=transfer_scalars)
         sim.set_state_zero()
         plan = sim.run(ops)
@@ -102,7 +147,7 @@ def _worker(rank, world, port, n, ops, transfer_scalars, out_dir):
         amp5 = sim.get_ampl(5)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), shard=eng.np, pos=np.array(sim.pos), norm=norm,
                  amp5=np.array([amp5.real, amp5.imag]), swaps=sim.stats.swaps, nplan=len(plan),
-                 bytes_sent=sim.stats.bytes_sent)
+                 bytes_sent=sim.stats.bytes_sent, local_swap_passes=sim.stats.local_swap_passes)
     finally:
         dist.destroy_process_group()
 
@@ -115,9 +160,9 @@ def free_port():
     return p
 
 
-def run_sharded(world, n, ops, tmp_path, transfer_scalars=1 << 28):
+def run_sharded(world, n, ops, tmp_path, transfer_scalars=1 << 28, p2p=False):
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, free_port(), n, ops, transfer_scalars, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, free_port(), n, ops, transfer_scalars, str(tmp_path), p2p), nprocs=world, join=True)
     g = world.bit_length() - 1
     n_local = n - g
     full = np.zeros(1 << n, np.complex64)
@@ -146,6 +191,21 @@ def test_sharded_random_circuit_matches_unsharded_oracle(world, tmp_path):
     a5 = res[0]["amp5"]
     assert abs(complex(a5[0], a5[1]) - want[5]) < 2e-6
     assert int(res[0]["swaps"]) >= 1 and int(res[0]["swaps"]) == int(res[0]["nplan"])
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_peer_memory_swap_path(world, tmp_path):
+    """the in-place peer-memory swap path (_swap_p2p): victims at any local bit, k > 1 exchanges, and the
+    local SWAP pass that first lifts victims sitting on the lowest bits (MIN_SWAP_BIT)."""
+    n = 10
+    g = world.bit_length() - 1
+    ops = random_ops(n, 48, seed=10 + world, max_local=n - g)
+    want = oracle_full(n, ops)
+    got, res = run_sharded(world, n, ops, tmp_path, p2p=True)
+    assert np.abs(got - want).max() < 2e-6
+    assert abs(float(res[0]["norm"]) - 1.0) < 1e-5
+    assert int(res[0]["swaps"]) >= 2 and int(res[0]["swaps"]) == int(res[0]["nplan"])
+    assert int(res[0]["local_swap_passes"]) >= 1  # random victims do land on the low bits
 
 
 def test_sharded_rqc_trace_world2(tmp_path):
