@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""A few passes through every fp32/fp64 gate kernel at small n, for `compute-sanitizer --tool memcheck|racecheck`."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qsim_b200
+
+def unitary(g, seed, cdt):
+    r = np.random.RandomState(seed)
+    a = r.standard_normal((1 << g, 1 << g)) + 1j * r.standard_normal((1 << g, 1 << g))
+    u, _ = np.linalg.qr(a)
+    return u.astype(cdt)
+
+n = 15
+for rdt, cdt in ((np.float32, np.complex64), (np.float64, np.complex128)):
+    ss, sim = qsim_b200.StateSpaceB200(rdt), qsim_b200.SimulatorB200(rdt)
+    st = ss.Create(n); ss.SetStateUniform(st)
+    for qs in ([3], [0, 7], [1, 4, 9], [5, 8, 11, 14], [0, 6, 9, 12], [0, 1, 2, 3], [1, 2, 7, 8], [4, 6, 8, 10, 12],
+               [0, 3, 5, 9, 13], [2, 4, 6, 8, 10, 12], [0, 1, 5, 9, 11, 14]):
+        u = unitary(len(qs), len(qs), cdt)
+        sim.ApplyGate(qs, u, st)
+        sim.ExpectationValue(qs, u, st)
+    sim.ApplyControlledGate([5, 9], [2, 12], 0b01, unitary(2, 7, cdt), st)
+    print(rdt.__name__, "norm", ss.Norm(st), "samples", ss.Sample(st, 8, 1)[:3], flush=True)
+    ss.Measure([0, 7], 0.3, st)
+ss.DeviceSync()
+print("done")
