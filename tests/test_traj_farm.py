@@ -60,8 +60,8 @@ def test_slices_add_up(circuit_file):
 @pytest.mark.gpu
 def test_b200_trajectories_match_reference_cpu(circuit_file):
     """same repetition ids => same Kraus choices => same observable sums (fp32 round-off apart)."""
-    if not os.path.exists(REF):
-        pytest.skip("oracle/_ref not built")
+    if not (os.path.exists(REF) and os.path.exists(traj_farm.BINARY)):
+        pytest.skip("oracle/_ref or apps/_bin not built (the reference tree was absent at build time)")
     for fused in (2, 4):
         ref = traj_farm.run_farm(circuit_file, 0, 16, gpus=1, p=0.05, max_fused_size=fused, binary=REF,
                                  device_ids=[None])
