@@ -113,11 +113,22 @@ int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) 
     if constexpr (!UNROLL) {
       return QB200_ERR_UNSUPPORTED;
     } else {
+      // Small read-only passes do almost no arithmetic: what matters is bytes in flight.  fp32 G <= 2 runs
+      // the software-pipelined loop (next group's loads issued before the current group is consumed) on a
+      // persistent grid of four 256-thread blocks per SM.
+      constexpr bool EPF = sizeof(FP) == 4 && G <= 2;
+      constexpr int EMINB = EPF ? 4 : MINB;
+      auto kern = k_gate_reg<FP, G, MODE, true, true, EPF, NT, EMINB, Mat>;
       uint32_t blocks = (uint32_t) (blocks64 < kExpectMaxBlocks ? blocks64 : kExpectMaxBlocks);
+      if constexpr (EPF) {
+        static const int occ = resident_blocks(kern, NT);
+        const uint64_t persistent = uint64_t{kNumSMs} * occ;
+        if (blocks > persistent) blocks = (uint32_t) persistent;
+      }
       int rc = ensure_scratch(ctx, (2 * size_t{blocks} + 2) * sizeof(double));
       if (rc) return rc;
       double* partials = (double*) ctx->scratch;
-      k_gate_reg<FP, G, MODE, true, true, false, NT, MINB, Mat><<<blocks, NT, 0, ctx->stream>>>(st, g, mat, partials);
+      kern<<<blocks, NT, 0, ctx->stream>>>(st, g, mat, partials);
       QB_LAUNCHED(ctx);
       return finish_expectation(ctx, partials, blocks, out);
     }
