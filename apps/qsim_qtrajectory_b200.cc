@@ -16,7 +16,7 @@
 // here: depolarizing noise after every gate qubit; observables = X_q and Z_q on every qubit
 // plus one 6-qubit Pauli string per window of 6 qubits.
 //
-//   [CUDA_VISIBLE_DEVICES=r] qsim_qtrajectory_b200 -c circuit -d maxtime -p 0.001 -0 traj0 -n num -f 4 [-v 0]
+//   [CUDA_VISIBLE_DEVICES=r] qsim_qtrajectory_b200 -c circuit -d maxtime -p 0.001 -0 traj0 -n num -f 4 [-v 0] [-b 1]
 // prints one JSON line: {"n":..,"traj0":..,"num":..,"seconds":..,"sums":[re,im,...]}
 #include <unistd.h>
 
@@ -46,6 +46,7 @@
 #include "formux.h"
 #include "simmux.h"
 #else
+#include "qsim_b200/expect_b200.h"
 #include "qsim_b200/simulator_b200.h"
 #endif
 
@@ -56,12 +57,15 @@ struct Options {
   unsigned maxtime = std::numeric_limits<unsigned>::max();
   double p = 0.001;
   unsigned traj0 = 0, num = 8, max_fused_size = 4, verbosity = 0, threads = 0;
+  // 1: all observables of a trajectory through qsim::ExpectationValues (expect_b200.h: one stream
+  // synchronisation per trajectory); 0: the reference's lib/expect.h, one synchronisation per string
+  unsigned batch = 1;
 };
 
 Options Parse(int argc, char* argv[]) {
   Options o;
   int k;
-  while ((k = getopt(argc, argv, "c:d:p:0:n:f:t:v:")) != -1) {
+  while ((k = getopt(argc, argv, "c:d:p:0:n:f:t:v:b:")) != -1) {
     switch (k) {
       case 'c': o.circuit_file = optarg; break;
       case 'd': o.maxtime = std::atoi(optarg); break;
@@ -71,9 +75,10 @@ Options Parse(int argc, char* argv[]) {
       case 'f': o.max_fused_size = std::atoi(optarg); break;
       case 't': o.threads = std::atoi(optarg); break;
       case 'v': o.verbosity = std::atoi(optarg); break;
+      case 'b': o.batch = std::atoi(optarg); break;
       default:
         std::fprintf(stderr, "usage: %s -c circuit [-d maxtime] [-p prob] [-0 traj0] [-n num] "
-                             "[-f max_fused_size] [-t threads] [-v verbosity]\n", argv[0]);
+                             "[-f max_fused_size] [-t threads] [-v verbosity] [-b batch]\n", argv[0]);
         std::exit(1);
     }
   }
@@ -127,6 +132,12 @@ struct Counting {
     return base.ExpectationValue(qs, m, s);
   }
   static unsigned SIMDRegisterSize() { return Base::SIMDRegisterSize(); }
+#ifndef QTRAJ_REFERENCE_CPU
+  void BeginExpectationBatch(unsigned expected) const { base.BeginExpectationBatch(expected); }
+  std::vector<std::complex<double>> EndExpectationBatch(unsigned max_count) const {
+    return base.EndExpectationBatch(max_count);
+  }
+#endif
   Base base;
 };
 
@@ -201,6 +212,13 @@ int main(int argc, char* argv[]) {
     if (!QTSimulator::RunOnce(param, ncircuit, uint64_t{opt.traj0} + i, state_space, simulator, state, stat)) {
       return 1;
     }
+#ifndef QTRAJ_REFERENCE_CPU
+    if (opt.batch) {
+      const auto evals = ExpectationValues<IO, Fuser>(observables, simulator, state);
+      for (std::size_t k = 0; k < observables.size(); ++k) sums[k] += evals[k];
+      continue;
+    }
+#endif
     for (std::size_t k = 0; k < observables.size(); ++k) {
       sums[k] += ExpectationValue<IO, Fuser>(observables[k], simulator, state);
     }

@@ -123,6 +123,16 @@ int qb200_apply_controlled_gate(qb200_ctx* ctx, int dtype, void* state, unsigned
 int qb200_expectation_value(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits,
                             const unsigned* qs, unsigned num_targets, const void* matrix,
                             double out_re_im[2]);
+/* Batched reductions (no reference counterpart: lib/expect.h:106-151 and
+ * lib/qtrajectory.h read one expectation value at a time, one stream synchronisation each).
+ * Between begin and end every reduction of this context -- qb200_expectation_value,
+ * qb200_norm, qb200_inner_product, qb200_real_inner_product -- is enqueued on the stream and
+ * returns at once with its `out` set to NaN; its result goes to the next slot of a mapped
+ * pinned host array.  `end` synchronises once and copies the `*count` results, (re, im) per
+ * slot in call order, to `out` (capacity in slots; QB200_ERR_INVALID if it is too small).
+ * `expected` only pre-sizes the slot array; it grows on demand. */
+int qb200_reduce_batch_begin(qb200_ctx* ctx, uint32_t expected);
+int qb200_reduce_batch_end(qb200_ctx* ctx, double* out, uint32_t capacity, uint32_t* count);
 
 /* ---- StateSpace (lib/statespace_cuda.h, lib/statespace.h) -------------- */
 int qb200_set_all_zeros(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits);      /* :109-112 */

@@ -44,6 +44,21 @@ class SimulatorB200 final {
     return {out[0], out[1]};
   }
 
+  // Batched expectation values (no reference counterpart; used by expect_b200.h): between Begin and End
+  // ExpectationValue enqueues its pass and returns NaN at once; End synchronises the stream once and
+  // returns the values in call order.
+  void BeginExpectationBatch(unsigned expected = 0) const {
+    QB200_CHECK(ctx(), qb200_reduce_batch_begin(ctx(), expected));
+  }
+  std::vector<std::complex<double>> EndExpectationBatch(unsigned max_count) const {
+    std::vector<double> buf(2 * std::size_t{max_count} + 2);
+    uint32_t count = 0;
+    QB200_CHECK(ctx(), qb200_reduce_batch_end(ctx(), buf.data(), max_count, &count));
+    std::vector<std::complex<double>> out(count);
+    for (uint32_t i = 0; i < count; ++i) out[i] = {buf[2 * i], buf[2 * i + 1]};
+    return out;
+  }
+
   // lib/simulator_cuda.h:265-267 (the reference's tests size their sweeps from it)
   static unsigned SIMDRegisterSize() { return 32; }
 

@@ -358,3 +358,19 @@ class SimulatorB200(_Base):
         if rc != ERR_UNSUPPORTED:
             self._check(rc, "ExpectationValue")
         return complex(out[0], out[1])
+
+    def ExpectationValues(self, terms, state: State) -> List[complex]:
+        """Batched expectation values (include/qsim_b200/expect_b200.h; no reference counterpart):
+        `terms` = [(qs, matrix), ...]; every read-only pass is enqueued back to back and the values are
+        read after ONE stream synchronisation.  Same kernels, same values as ExpectationValue per term."""
+        terms = list(terms)
+        self._check(self._lib.qb200_reduce_batch_begin(self._ctx, len(terms)), "reduce_batch_begin")
+        try:
+            for qs, matrix in terms:
+                self.ExpectationValue(qs, matrix, state)
+        finally:
+            out = (C.c_double * (2 * len(terms) + 2))()
+            count = C.c_uint32()
+            rc = self._lib.qb200_reduce_batch_end(self._ctx, out, len(terms), C.byref(count))
+        self._check(rc, "reduce_batch_end")
+        return [complex(out[2 * i], out[2 * i + 1]) for i in range(count.value)]

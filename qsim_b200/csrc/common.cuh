@@ -38,6 +38,8 @@ struct Tuning {
   int tcx = -1;            // fp32 G=6 gates and G=4..6 expectation values on the tensor cores: 0 off
   int tc_comp6 = 276;      // accumulation-bias compensation of the G=6 tensor-core gate, in units of 1e-9
   int tc_low = -1;         // -1: per-layout rule (gate_launch.cuh); k >= 0: G=4 on the tensor cores iff lowest non-zero target >= k
+  int expect_ug = -1;      // fp32 G<=2 expectation values (k_expect_stream): -1/1 = one group per thread per iteration;
+                           // 2 = several groups, grid-strided; 3 = several groups, contiguous per block (both slower)
   int big = -1;            // -1 auto (on); 0 = fp32 G>=5 through the register/generic kernels;
                            // 1/2/3 = alternative launch shapes of k_gate_big (tools/microbench.py)
 };
@@ -52,6 +54,10 @@ struct qb200_ctx {
   void* pinned = nullptr;         // pinned host result slot
   size_t pinned_bytes = 0;
   void* d_mat = nullptr;          // device copy of matrices too big for kernel parameters
+  double* res = nullptr;          // mapped pinned result slots (re, im): the final reduction kernel writes here
+  uint32_t res_cap = 0;           // slots allocated
+  bool batching = false;          // reductions are enqueued without synchronising (qb200_reduce_batch_begin/end)
+  uint32_t batch_count = 0;       // slots filled by the open batch
   int last_error = 0;             // cudaError_t
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

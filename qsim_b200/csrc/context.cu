@@ -3,6 +3,7 @@
 // lib/simulator_cuda.h:52-62 / lib/statespace_cuda.h:378-390).
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <new>
 
 #include "gate_launch.cuh"
@@ -111,17 +112,42 @@ k_sum_partials2(const double* __restrict__ partials, uint32_t count, double* __r
   }
 }
 
-// partials[0 .. 2*blocks) -> out[2] on the host (synchronises the stream).
+// Result slots: mapped pinned host memory the final reduction kernel writes straight into
+// (no device->host copy on the stream).
+int ensure_results(qb200_ctx* ctx, uint32_t slots) {
+  if (slots <= ctx->res_cap) return QB200_OK;
+  uint32_t want = 64;
+  while (want < slots) want <<= 1;
+  double* fresh = nullptr;
+  QB_CUDA(ctx, cudaHostAlloc((void**) &fresh, size_t{want} * 2 * sizeof(double),
+                             cudaHostAllocMapped | cudaHostAllocPortable));
+  if (ctx->res) {
+    // results of an open batch stay valid: finish what is in flight, carry the filled slots over
+    QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(fresh, ctx->res, size_t{ctx->batch_count} * 2 * sizeof(double));
+    QB_CUDA(ctx, cudaFreeHost(ctx->res));
+  }
+  ctx->res = fresh;
+  ctx->res_cap = want;
+  return QB200_OK;
+}
+
+// partials[0 .. 2*blocks) -> out[2] on the host (synchronises the stream); inside a batch
+// (qb200_reduce_batch_begin) -> the next result slot, no synchronisation, `out` = NaN.
 int finish_expectation(qb200_ctx* ctx, double* partials, uint32_t blocks, double out[2]) {
-  double* dres = partials + 2 * size_t{blocks};
-  k_sum_partials2<<<1, 256, 0, ctx->stream>>>(partials, blocks, dres);
-  QB_LAUNCHED(ctx);
-  int rc = ensure_pinned(ctx, 2 * sizeof(double));
+  const uint32_t slot = ctx->batching ? ctx->batch_count : 0;
+  int rc = ensure_results(ctx, slot + 1);
   if (rc) return rc;
-  QB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, dres, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  k_sum_partials2<<<1, 256, 0, ctx->stream>>>(partials, blocks, ctx->res + 2 * size_t{slot});
+  QB_LAUNCHED(ctx);
+  if (ctx->batching) {
+    ++ctx->batch_count;
+    if (out) out[0] = out[1] = std::numeric_limits<double>::quiet_NaN();
+    return QB200_OK;
+  }
   QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  out[0] = ((double*) ctx->pinned)[0];
-  out[1] = ((double*) ctx->pinned)[1];
+  out[0] = ctx->res[0];
+  out[1] = ctx->res[1];
   return QB200_OK;
 }
 
@@ -166,6 +192,7 @@ int qb200_ctx_destroy(qb200_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->res) cudaFreeHost(ctx->res);
     if (ctx->d_mat) {
       MatRing* r = (MatRing*) ctx->d_mat;
       for (int i = 0; i < kMatSlots; ++i)
@@ -203,6 +230,7 @@ int qb200_ctx_set_tuning(qb200_ctx* ctx, const char* key, int value) {
   else if (!std::strcmp(key, "tile")) ctx->tune.tile = value;
   else if (!std::strcmp(key, "prefetch")) ctx->tune.prefetch = value;
   else if (!std::strcmp(key, "big")) ctx->tune.big = value;
+  else if (!std::strcmp(key, "expect_ug")) ctx->tune.expect_ug = value;
   else if (!std::strcmp(key, "tc")) ctx->tune.tc = value;
   else if (!std::strcmp(key, "tc_low")) ctx->tune.tc_low = value;
   else if (!std::strcmp(key, "tcx")) ctx->tune.tcx = value;
@@ -284,6 +312,29 @@ int qb200_device_sync(void) {
     (void) cudaGetLastError();
     return QB200_ERR_CUDA;
   }
+  return QB200_OK;
+}
+
+int qb200_reduce_batch_begin(qb200_ctx* ctx, uint32_t expected) {
+  if (!ctx || ctx->batching) return QB200_ERR_INVALID;
+  DeviceGuard guard(ctx);
+  int rc = ensure_results(ctx, expected ? expected : 1);
+  if (rc) return rc;
+  ctx->batching = true;
+  ctx->batch_count = 0;
+  return QB200_OK;
+}
+
+int qb200_reduce_batch_end(qb200_ctx* ctx, double* out, uint32_t capacity, uint32_t* count) {
+  if (!ctx || !ctx->batching || (capacity && !out)) return QB200_ERR_INVALID;
+  DeviceGuard guard(ctx);
+  ctx->batching = false;
+  const uint32_t n = ctx->batch_count;
+  ctx->batch_count = 0;
+  if (count) *count = n;
+  QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n > capacity) return QB200_ERR_INVALID;
+  std::memcpy(out, ctx->res, size_t{n} * 2 * sizeof(double));
   return QB200_OK;
 }
 

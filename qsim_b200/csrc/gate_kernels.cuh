@@ -286,6 +286,94 @@ k_gate_reg(FP* __restrict__ st, const __grid_constant__ Geom g,
 }
 
 // ---------------------------------------------------------------------------
+// Streaming expectation kernel for small gates (fp32 G <= 2): a read-only pass
+// with almost no arithmetic, so what sets its speed is the number of bytes each
+// thread keeps in flight.  UG independent groups (grid-strided, so every access
+// stays coalesced) are loaded per iteration, chosen by the launcher so that a
+// thread issues four 128-bit (or 64-bit, kV1) loads per iteration whatever the
+// layout, and the next iteration's loads are issued before the current one is
+// consumed.  Persistent grid.  Arithmetic as in k_gate_reg<EXPECT>: products in
+// FP, accumulation in double (lib/simulator_basic.h:323-324).
+// ---------------------------------------------------------------------------
+template <typename FP, int G, int MODE, int UG, int NT, int MINB, typename Mat>
+__global__ void __launch_bounds__(NT, MINB)
+k_expect_stream(const FP* __restrict__ st, const __grid_constant__ Geom g,
+                const __grid_constant__ Mat mat, double* __restrict__ partials, const int contiguous) {
+  constexpr int N = 1 << G;
+  constexpr int NV = MODE == kV2 ? 2 : 1;
+  using C = typename CT<FP>::type;
+  double ere = 0, eim = 0;
+  // a thread's UG groups per iteration: NT apart inside the block's contiguous chunk of UG * NT work items
+  // (`contiguous`), or one grid stride apart
+  const uint64_t stride = contiguous ? uint64_t{NT} : uint64_t{gridDim.x} * NT;
+  const uint64_t advance = uint64_t{gridDim.x} * NT * UG;
+
+  // branch-free: a group beyond the end re-reads the thread's first (valid) group and is zeroed by selects,
+  // so all of an iteration's loads issue back to back
+  auto load = [&](uint64_t i, C (&x)[UG][NV][N]) {
+#pragma unroll
+    for (int u = 0; u < UG; ++u) {
+      const uint64_t iu = i + u * stride;
+      const bool ok = u == 0 || iu < g.work;
+      const FP* p = st + 2 * expand_index(ok ? iu : i, g);
+      if constexpr (MODE == kV1) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) x[u][0][k] = ldc1<FP>(p + 2 * elem_offset<G>(k, g));
+      } else if constexpr (MODE == kV2) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) ldc2<FP>(p + 2 * elem_offset<G>(k, g), x[u][0][k], x[u][1][k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < N; k += 2) ldc2<FP>(p + 2 * elem_offset<G>(k, g), x[u][0][k], x[u][0][k + 1]);
+      }
+      if (u > 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+          for (int k = 0; k < N; ++k) x[u][v][k] = ok ? x[u][v][k] : CT<FP>::make(0, 0);  // contributes nothing
+      }
+    }
+  };
+
+  uint64_t i = blockIdx.x * uint64_t{NT} * (contiguous ? UG : 1) + threadIdx.x;
+  C xn[UG][NV][N];
+  if (i < g.work) load(i, xn);
+  for (; i < g.work; i += advance) {
+    C x[UG][NV][N];
+#pragma unroll
+    for (int u = 0; u < UG; ++u)
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < N; ++k) x[u][v][k] = xn[u][v][k];
+    if (i + advance < g.work) load(i + advance, xn);
+#pragma unroll
+    for (int u = 0; u < UG; ++u) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        C ix[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) ix[k] = CT<FP>::rot(x[u][v][k]);
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+          FP re, im, xr, xi;
+          CT<FP>::get(row_dot<FP, G>(x[u][v], ix, mat, r), re, im);
+          CT<FP>::get(x[u][v][r], xr, xi);
+          ere += xr * re + xi * im;
+          eim += xr * im - xi * re;
+        }
+      }
+    }
+  }
+
+  block_sum2<NT>(ere, eim);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = ere;
+    partials[2 * blockIdx.x + 1] = eim;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Runtime-generic kernel: any G <= 6, any dtype; each thread's group lives in
 // shared memory (column-major over threads -> conflict free), matrix read from
 // global memory through the read-only path.  Used for fp32 G=6, fp64 G>=5 and

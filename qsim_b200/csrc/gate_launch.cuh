@@ -113,22 +113,35 @@ int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) 
     if constexpr (!UNROLL) {
       return QB200_ERR_UNSUPPORTED;
     } else {
-      // Small read-only passes do almost no arithmetic: what matters is bytes in flight.  fp32 G <= 2 runs
-      // the software-pipelined loop (next group's loads issued before the current group is consumed) on a
-      // persistent grid of four 256-thread blocks per SM.
-      constexpr bool EPF = sizeof(FP) == 4 && G <= 2;
-      constexpr int EMINB = EPF ? 4 : MINB;
-      auto kern = k_gate_reg<FP, G, MODE, true, true, EPF, NT, EMINB, Mat>;
       uint32_t blocks = (uint32_t) (blocks64 < kExpectMaxBlocks ? blocks64 : kExpectMaxBlocks);
-      if constexpr (EPF) {
-        static const int occ = resident_blocks(kern, NT);
-        const uint64_t persistent = uint64_t{kNumSMs} * occ;
-        if (blocks > persistent) blocks = (uint32_t) persistent;
+      // Small read-only passes: fp32 G <= 2 runs k_expect_stream (the next iteration's loads issued before the
+      // current group is consumed) on a persistent grid of four 256-thread blocks per SM.  One group per thread
+      // per iteration is the default: several groups per iteration (tuning expect_ug = 2 grid-strided, 3
+      // contiguous per block) measured 15-25 % slower at n = 26 and 30 in every layout
+      // (profiles/r01_expect_variants.txt) -- the pass is not short of bytes in flight.
+      if constexpr (sizeof(FP) == 4 && G <= 2) {
+        constexpr int kLoads = MODE == kV2T ? (1 << G) / 2 : (1 << G);  // per group
+        constexpr int kUG = kLoads >= 4 ? 1 : 4 / kLoads;
+        auto run = [&](auto kern, int occ, int ug, int contiguous) -> int {
+          const uint64_t persistent = uint64_t{kNumSMs} * occ;
+          const uint64_t need = (blocks64 + ug - 1) / ug;
+          const uint32_t nb = (uint32_t) (need < persistent ? need : persistent);
+          int rc = ensure_scratch(ctx, (2 * size_t{nb} + 2) * sizeof(double));
+          if (rc) return rc;
+          double* partials = (double*) ctx->scratch;
+          kern<<<nb, NT, 0, ctx->stream>>>(st, g, mat, partials, contiguous);
+          QB_LAUNCHED(ctx);
+          return finish_expectation(ctx, partials, nb, out);
+        };
+        static const int occ1 = resident_blocks(k_expect_stream<FP, G, MODE, 1, NT, 4, Mat>, NT);
+        static const int occu = resident_blocks(k_expect_stream<FP, G, MODE, kUG, NT, 4, Mat>, NT);
+        if (kUG == 1 || ctx->tune.expect_ug < 2) return run(k_expect_stream<FP, G, MODE, 1, NT, 4, Mat>, occ1, 1, 0);
+        return run(k_expect_stream<FP, G, MODE, kUG, NT, 4, Mat>, occu, kUG, ctx->tune.expect_ug == 2 ? 0 : 1);
       }
       int rc = ensure_scratch(ctx, (2 * size_t{blocks} + 2) * sizeof(double));
       if (rc) return rc;
       double* partials = (double*) ctx->scratch;
-      kern<<<blocks, NT, 0, ctx->stream>>>(st, g, mat, partials);
+      k_gate_reg<FP, G, MODE, true, true, false, NT, MINB, Mat><<<blocks, NT, 0, ctx->stream>>>(st, g, mat, partials);
       QB_LAUNCHED(ctx);
       return finish_expectation(ctx, partials, blocks, out);
     }

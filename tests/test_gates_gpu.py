@@ -129,6 +129,34 @@ def test_expectation_value_matches_oracle(oracle, cdt, n):
             assert np.array_equal(ss.to_numpy(st), host)
 
 
+@pytest.mark.parametrize("cdt", [np.complex64, np.complex128])
+def test_batched_expectation_values_equal_single_calls(oracle, cdt):
+    """qb200_reduce_batch_begin/end (include/qsim_b200/expect_b200.h): the passes of a batch are the
+    same kernels in the same order, read after one synchronisation -> bit-identical values; the
+    batch also survives growing past its pre-sized slot array and leaves the context usable."""
+    ss, sim = backends(cdt)
+    n = 14
+    host = random_state(n, cdt, seed=5)
+    st = ss.Create(n)
+    ss.from_numpy(host, st)
+    terms = []
+    for rep in range(3):  # 3 x 60 terms > the 64 slots allocated first
+        for g in range(1, 7):
+            for k, qs in enumerate(target_sets(n, g)):
+                terms.append((qs, random_matrix(g, seed=100 * rep + g + k, cdtype=cdt)))
+    single = [sim.ExpectationValue(qs, m, st) for qs, m in terms]
+    batch = sim.ExpectationValues(terms[:7], st) + sim.ExpectationValues(terms[7:], st)
+    assert len(batch) == len(terms)
+    assert batch == single
+    want = oracle.expectation_value(host, terms[0][0], terms[0][1])
+    assert abs(batch[0] - want) <= (1e-6 if cdt == np.complex64 else 1e-13)
+    assert sim.ExpectationValues([], st) == []
+    # a batch cannot be opened twice, and ending without begin is an error, not a hang
+    assert sim._lib.qb200_reduce_batch_end(sim._ctx, None, 0, None) != 0
+    assert sim.ExpectationValue(terms[0][0], terms[0][1], st) == single[0]
+    assert np.array_equal(ss.to_numpy(st), host)
+
+
 def test_gate_application_is_deterministic():
     """EXPECT_EQ bit-identical amplitudes across repeated runs
     (tests/simulator_testfixture.h:735-764)."""

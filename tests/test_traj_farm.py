@@ -70,3 +70,8 @@ def test_b200_trajectories_match_reference_cpu(circuit_file):
         err = np.abs(np.array(got["sums"]) - np.array(ref["sums"])).max()
         assert err < 16 * 2e-5, err
         assert np.abs(np.array(ref["mean"])).max() > 0.1
+        # default = all observables of a trajectory in one batch (expect_b200.h); "-b 0" = the reference's
+        # lib/expect.h, one synchronisation per operator string: same kernels, identical sums
+        serial = traj_farm.run_farm(circuit_file, 0, 16, gpus=1, p=0.05, max_fused_size=fused,
+                                    extra_args=("-b", "0"))
+        assert serial["sums"] == got["sums"] and serial["expect_passes"] == got["expect_passes"]

@@ -25,6 +25,9 @@ ap.add_argument("--fused", type=int, default=4)
 ap.add_argument("--p", type=float, default=0.001)
 ap.add_argument("--procs-per-gpu", type=int, default=1,
                 help="worker processes per GPU (time-sliced: fills the host-side gaps between a trajectory's launches)")
+ap.add_argument("--batch", type=int, default=1,
+                help="1: all observables of a trajectory in one batch (expect_b200.h, one stream synchronisation); "
+                     "0: the reference's lib/expect.h loop, one synchronisation per operator string")
 args = ap.parse_args()
 
 with tempfile.NamedTemporaryFile("w", suffix=f"_rqc_q{args.n}", delete=False) as f:
@@ -32,7 +35,8 @@ with tempfile.NamedTemporaryFile("w", suffix=f"_rqc_q{args.n}", delete=False) as
     path = f.name
 ppg = args.procs_per_gpu
 res = run_farm(path, 0, args.num * args.gpus, gpus=args.gpus * ppg, p=args.p, max_fused_size=args.fused,
-               device_ids=[d for d in range(args.gpus) for _ in range(ppg)])
+               device_ids=[d for d in range(args.gpus) for _ in range(ppg)], extra_args=("-b", str(args.batch)))
+res["batch"] = args.batch
 res["procs_per_gpu"] = ppg
 os.unlink(path)
 res.pop("sums")
