@@ -57,9 +57,10 @@ struct Options {
   unsigned maxtime = std::numeric_limits<unsigned>::max();
   double p = 0.001;
   unsigned traj0 = 0, num = 8, max_fused_size = 4, verbosity = 0, threads = 0;
-  // 1: all observables of a trajectory through qsim::ExpectationValues (expect_b200.h: one stream
-  // synchronisation per trajectory); 0: the reference's lib/expect.h, one synchronisation per string
-  unsigned batch = 1;
+  // 2 (default): all observables of a trajectory through qsim::ExpectationValues (expect_b200.h: single-qubit
+  // operators from the reduced density matrices, the rest batched, one stream synchronisation); 1: batched
+  // only (same kernels and values as 0); 0: the reference's lib/expect.h, one synchronisation per string
+  unsigned batch = 2;
 };
 
 Options Parse(int argc, char* argv[]) {
@@ -108,7 +109,7 @@ std::vector<std::vector<qsim::OpString<FP>>> Observables(unsigned n) {
 
 // Counts the passes the drivers issue (algorithmic HBM bytes of the run):
 // gate pass = 16 * 2^n B, expectation pass = 8 * 2^n B in fp32.
-struct PassCount { uint64_t gates = 0, expects = 0; };
+struct PassCount { uint64_t gates = 0, expects = 0, moment_calls = 0; };
 PassCount g_passes;
 
 template <typename Base>
@@ -134,6 +135,10 @@ struct Counting {
   static unsigned SIMDRegisterSize() { return Base::SIMDRegisterSize(); }
 #ifndef QTRAJ_REFERENCE_CPU
   void BeginExpectationBatch(unsigned expected) const { base.BeginExpectationBatch(expected); }
+  std::vector<double> OneQubitMoments(const State& s) const {
+    g_passes.moment_calls += 1;
+    return base.OneQubitMoments(s);
+  }
   std::vector<std::complex<double>> EndExpectationBatch(unsigned max_count) const {
     return base.EndExpectationBatch(max_count);
   }
@@ -214,7 +219,7 @@ int main(int argc, char* argv[]) {
     }
 #ifndef QTRAJ_REFERENCE_CPU
     if (opt.batch) {
-      const auto evals = ExpectationValues<IO, Fuser>(observables, simulator, state);
+      const auto evals = ExpectationValues<IO, Fuser>(observables, simulator, state, opt.batch >= 2);
       for (std::size_t k = 0; k < observables.size(); ++k) sums[k] += evals[k];
       continue;
     }
@@ -226,9 +231,10 @@ int main(int argc, char* argv[]) {
   const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
   std::printf("{\"n\": %u, \"traj0\": %u, \"num\": %u, \"num_ops\": %zu, \"num_observables\": %zu, "
-              "\"gate_passes\": %llu, \"expect_passes\": %llu, \"seconds\": %.6f, \"sums\": [",
+              "\"gate_passes\": %llu, \"expect_passes\": %llu, \"moment_calls\": %llu, \"seconds\": %.6f, \"sums\": [",
               circuit.num_qubits, opt.traj0, opt.num, ncircuit.ops.size(), observables.size(),
-              (unsigned long long) g_passes.gates, (unsigned long long) g_passes.expects, seconds);
+              (unsigned long long) g_passes.gates, (unsigned long long) g_passes.expects,
+              (unsigned long long) g_passes.moment_calls, seconds);
   for (std::size_t k = 0; k < sums.size(); ++k) {
     std::printf("%s%.9g, %.9g", k ? ", " : "", sums[k].real(), sums[k].imag());
   }

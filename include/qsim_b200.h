@@ -131,6 +131,13 @@ int qb200_expectation_value(qb200_ctx* ctx, int dtype, const void* state, unsign
  * pinned host array.  `end` synchronises once and copies the `*count` results, (re, im) per
  * slot in call order, to `out` (capacity in slots; QB200_ERR_INVALID if it is too small).
  * `expected` only pre-sizes the slot array; it grows on demand. */
+/* Reduced density matrices of ALL qubits in a handful of read-only passes (3 at 26 qubits, 4 at 30) instead
+ * of one pass per single-qubit operator (no reference counterpart; csrc/moments.cu).  out[4q .. 4q+3] =
+ * S00, S11, Re S01, Im S01 of qubit q with S00 / S11 = sum |a_i|^2 over bit_q(i) = 0 / 1 and
+ * S01 = sum conj(a_i0) a_i1 over the pairs i1 = i0 | 1 << q, so that for any 2x2 operator M on q
+ * <psi|M|psi> = m00 S00 + m11 S11 + m01 S01 + m10 conj(S01).  Products in the state's precision,
+ * accumulation in double.  Synchronises.  QB200_ERR_UNSUPPORTED for a state that is not 16-byte aligned. */
+int qb200_one_qubit_moments(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits, double* out);
 int qb200_reduce_batch_begin(qb200_ctx* ctx, uint32_t expected);
 int qb200_reduce_batch_end(qb200_ctx* ctx, double* out, uint32_t capacity, uint32_t* count);
 

@@ -2,8 +2,12 @@
 // operator strings) for SimulatorB200: the same host logic per string (weight-only strings,
 // single operators as they are, longer strings fused with max_fused_size = 6 into one gate), but
 // the read-only passes of ALL observables are enqueued back to back and read after ONE stream
-// synchronisation instead of one per operator string.  Values are identical to
-// calling qsim::ExpectationValue<IO, Fuser> per observable: the same kernels run in the same order.
+// synchronisation instead of one per operator string, and -- when there are at
+// least kMomentsThreshold of them -- all single-qubit operators are evaluated from the reduced density
+// matrices of the qubits (SimulatorB200::OneQubitMoments: 3-4 passes for every qubit together instead
+// of one pass per operator).  With `use_moments` = false the values are identical to calling
+// qsim::ExpectationValue<IO, Fuser> per observable (the same kernels in the same order); with the
+// moments they agree to the precision contract (products in FP, sums in double; |delta| ~ 1e-7 in fp32).
 #ifndef QSIM_B200_EXPECT_B200_H_
 #define QSIM_B200_EXPECT_B200_H_
 
@@ -15,6 +19,8 @@
 
 namespace qsim {
 
+constexpr std::size_t kMomentsThreshold = 6;
+
 /**
  * Expectation values of several observables, each a sum of weighted operator strings
  * (argument meaning as in lib/expect.h:95-104).  An observable whose strings cannot be
@@ -23,7 +29,7 @@ namespace qsim {
 template <typename IO, typename Fuser, typename FP, typename Simulator>
 std::vector<std::complex<double>> ExpectationValues(
     const std::vector<std::vector<OpString<FP>>>& observables,
-    const Simulator& simulator, const typename Simulator::State& state) {
+    const Simulator& simulator, const typename Simulator::State& state, bool use_moments = true) {
   struct Term {
     std::size_t observable;
     std::complex<double> weight;
@@ -35,8 +41,14 @@ std::vector<std::complex<double>> ExpectationValues(
   typename Fuser::Parameter param;
   param.max_fused_size = 6;
 
-  std::size_t expected = 0;
-  for (const auto& strings : observables) expected += strings.size();
+  std::size_t expected = 0, single = 0;
+  for (const auto& strings : observables) {
+    expected += strings.size();
+    for (const auto& str : strings) single += str.ops.size() == 1 && str.ops[0].qubits.size() == 1;
+  }
+  std::vector<double> moments;  // S00, S11, Re S01, Im S01 per qubit
+  if (use_moments && single >= kMomentsThreshold) moments = simulator.OneQubitMoments(state);
+
   simulator.BeginExpectationBatch((unsigned) expected);
 
   for (std::size_t k = 0; k < observables.size(); ++k) {
@@ -45,6 +57,14 @@ std::vector<std::complex<double>> ExpectationValues(
         evals[k] += str.weight;
       } else if (str.ops.size() == 1) {
         const auto& op = str.ops[0];
+        if (!moments.empty() && op.qubits.size() == 1) {
+          // <M> = m00 S00 + m11 S11 + m01 S01 + m10 conj(S01); matrix row-major, interleaved (lib/matrix.h:26-33)
+          const double* s = &moments[4 * std::size_t{op.qubits[0]}];
+          const std::complex<double> s01(s[2], s[3]);
+          const auto m = [&](int i) { return std::complex<double>(op.matrix[2 * i], op.matrix[2 * i + 1]); };
+          evals[k] += str.weight * (m(0) * s[0] + m(3) * s[1] + m(1) * s01 + m(2) * std::conj(s01));
+          continue;
+        }
         (void) simulator.ExpectationValue(op.qubits, op.matrix.data(), state);
         terms.push_back({k, str.weight});
       } else {

@@ -59,6 +59,17 @@ class SimulatorB200 final {
     return out;
   }
 
+  // Reduced density matrices of all qubits from 3-4 read-only passes (qb200_one_qubit_moments): 4 doubles per
+  // qubit, S00, S11, Re S01, Im S01.  Empty when the state cannot take the path (unaligned wrapped memory).
+  std::vector<double> OneQubitMoments(const State& state) const {
+    std::vector<double> out(4 * std::size_t{state.num_qubits()} + 4);
+    int rc = qb200_one_qubit_moments(ctx(), b200::DType<FP>::value, state.get(), state.num_qubits(), out.data());
+    if (rc == QB200_ERR_UNSUPPORTED) return {};
+    QB200_CHECK(ctx(), rc);
+    out.resize(4 * std::size_t{state.num_qubits()});
+    return out;
+  }
+
   // lib/simulator_cuda.h:265-267 (the reference's tests size their sweeps from it)
   static unsigned SIMDRegisterSize() { return 32; }
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "qb200_apply_gate": (_i, [_vp, _i, _vp, _u, _pu, _u, _vp]),
     "qb200_apply_controlled_gate": (_i, [_vp, _i, _vp, _u, _pu, _u, _pu, _u, _u64, _vp]),
     "qb200_expectation_value": (_i, [_vp, _i, _vp, _u, _pu, _u, _vp, _pd]),
+    "qb200_one_qubit_moments": (_i, [_vp, _i, _vp, _u, _pd]),
     "qb200_reduce_batch_begin": (_i, [_vp, C.c_uint32]),
     "qb200_reduce_batch_end": (_i, [_vp, _pd, C.c_uint32, C.POINTER(C.c_uint32)]),
     "qb200_set_all_zeros": (_i, [_vp, _i, _vp, _u]),

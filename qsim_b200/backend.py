@@ -359,6 +359,23 @@ class SimulatorB200(_Base):
             self._check(rc, "ExpectationValue")
         return complex(out[0], out[1])
 
+    def OneQubitMoments(self, state: State) -> np.ndarray:
+        """qb200_one_qubit_moments (csrc/moments.cu; no reference counterpart): array [n, 4] of
+        S00, S11, Re S01, Im S01 per qubit -- every single-qubit reduced density matrix from 3-4 read-only
+        passes.  <M_q> = m00 S00 + m11 S11 + m01 S01 + m10 conj(S01)."""
+        n = state.num_qubits()
+        out = np.zeros((max(n, 1), 4), dtype=np.float64)
+        rc = self._lib.qb200_one_qubit_moments(self._ctx, self._dt, state.get(), n, out.ctypes.data_as(_lib._pd))
+        self._check(rc, "OneQubitMoments")
+        return out[:n]
+
+    @staticmethod
+    def moment_expectation(moments_q, matrix) -> complex:
+        """<M> of a 2x2 operator from one row of OneQubitMoments."""
+        m = np.asarray(matrix, dtype=np.complex128).reshape(2, 2)
+        s01 = complex(moments_q[2], moments_q[3])
+        return complex(m[0, 0] * moments_q[0] + m[1, 1] * moments_q[1] + m[0, 1] * s01 + m[1, 0] * s01.conjugate())
+
     def ExpectationValues(self, terms, state: State) -> List[complex]:
         """Batched expectation values (include/qsim_b200/expect_b200.h; no reference counterpart):
         `terms` = [(qs, matrix), ...]; every read-only pass is enqueued back to back and the values are

@@ -38,11 +38,14 @@ def merge(results):
     gate_passes = sum(r.get("gate_passes", 0) for r in results)
     expect_passes = sum(r.get("expect_passes", 0) for r in results)
     # algorithmic bytes (fp32): gate pass 16*2^n, expectation pass 8*2^n, SetStateZero 8*2^n per trajectory
+    # (the 3-4 read passes of a OneQubitMoments call are not counted: the figure drops when they replace
+    # one pass per operator -- compare trajectories/s)
     abytes = (16.0 * gate_passes + 8.0 * expect_passes + 8.0 * num) * (1 << n)
     return {
         "n": n, "num": num, "slices": [(r["traj0"], r["num"], r["seconds"]) for r in results],
         "seconds": slowest, "trajectories_per_s": num / slowest if slowest > 0 else float("nan"),
         "gate_passes": gate_passes, "expect_passes": expect_passes,
+        "moment_calls": sum(r.get("moment_calls", 0) for r in results),
         "algorithmic_GBps": abytes / slowest / 1e9 if slowest > 0 else float("nan"),
         "mean": [s / num for s in sums], "sums": sums,
     }

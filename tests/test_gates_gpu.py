@@ -157,6 +157,35 @@ def test_batched_expectation_values_equal_single_calls(oracle, cdt):
     assert np.array_equal(ss.to_numpy(st), host)
 
 
+@pytest.mark.parametrize("cdt", [np.complex64, np.complex128])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 11, 12, 13, 15, 17, 20, 21])
+def test_one_qubit_moments(oracle, cdt, n):
+    """qb200_one_qubit_moments (csrc/moments.cu): S00, S11, S01 of every qubit against numpy in double, and
+    <M_q> rebuilt from them against the oracle's ExpectationValue (lib/simulator_basic.h:296-342) and the
+    per-operator kernel; tile layouts: one partial tile (n <= 12 / 11), several passes with filler bits."""
+    ss, sim = backends(cdt)
+    host = random_state(n, cdt, seed=50 + n)
+    st = ss.Create(n)
+    ss.from_numpy(host, st)
+    got = sim.OneQubitMoments(st)
+    assert got.shape == (n, 4)
+    psi = host.astype(np.complex128)
+    tol = 2e-6 if cdt == np.complex64 else 1e-13
+    for q in range(n):
+        v = psi.reshape(1 << (n - 1 - q), 2, 1 << q)
+        a0, a1 = v[:, 0, :].ravel(), v[:, 1, :].ravel()
+        s01 = np.vdot(a0, a1)
+        want = [np.vdot(a0, a0).real, np.vdot(a1, a1).real, s01.real, s01.imag]
+        assert np.abs(got[q] - np.array(want)).max() <= tol, (n, q, got[q], want)
+    for q in sorted({0, n // 2, n - 1}):
+        m = random_matrix(1, seed=q, cdtype=cdt)
+        rebuilt = sim.moment_expectation(got[q], m)
+        assert abs(rebuilt - oracle.expectation_value(host, [q], m)) <= tol * 4
+        assert abs(rebuilt - sim.ExpectationValue([q], m, st)) <= tol * 4
+    assert np.array_equal(ss.to_numpy(st), host)  # read-only
+    assert np.array_equal(sim.OneQubitMoments(st), got)  # deterministic
+
+
 def test_gate_application_is_deterministic():
     """EXPECT_EQ bit-identical amplitudes across repeated runs
     (tests/simulator_testfixture.h:735-764)."""

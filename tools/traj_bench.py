@@ -25,8 +25,9 @@ ap.add_argument("--fused", type=int, default=4)
 ap.add_argument("--p", type=float, default=0.001)
 ap.add_argument("--procs-per-gpu", type=int, default=1,
                 help="worker processes per GPU (time-sliced: fills the host-side gaps between a trajectory's launches)")
-ap.add_argument("--batch", type=int, default=1,
-                help="1: all observables of a trajectory in one batch (expect_b200.h, one stream synchronisation); "
+ap.add_argument("--batch", type=int, default=2,
+                help="2: single-qubit observables from the reduced density matrices (csrc/moments.cu) + the rest in one "
+                     "batch; 1: all observables of a trajectory in one batch (expect_b200.h, one stream synchronisation); "
                      "0: the reference's lib/expect.h loop, one synchronisation per operator string")
 args = ap.parse_args()
 
