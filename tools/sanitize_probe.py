@@ -23,5 +23,14 @@ for rdt, cdt in ((np.float32, np.complex64), (np.float64, np.complex128)):
     sim.ApplyControlledGate([5, 9], [2, 12], 0b01, unitary(2, 7, cdt), st)
     print(rdt.__name__, "norm", ss.Norm(st), "samples", ss.Sample(st, 8, 1)[:3], flush=True)
     ss.Measure([0, 7], 0.3, st)
+    # batched reductions (mapped pinned result slots) and the all-qubit moments kernel (3 passes at n = 15 / 14)
+    terms = [(qs, unitary(len(qs), 3, cdt)) for qs in ([2], [0, 9], [1, 5, 9, 13, 14], [0, 1, 5, 9, 11, 14])] * 20
+    vals = sim.ExpectationValues(terms, st)
+    mom = sim.OneQubitMoments(st)
+    st13 = ss.Create(13); ss.SetStateUniform(st13)
+    mom13 = sim.OneQubitMoments(st13)
+    st3 = ss.Create(3); ss.SetStateUniform(st3)
+    mom3 = sim.OneQubitMoments(st3)
+    print(rdt.__name__, "batched", len(vals), "moments", mom.shape, float(mom[:, :2].sum(axis=1).max()), mom13.shape, mom3.shape, flush=True)
 ss.DeviceSync()
 print("done")
