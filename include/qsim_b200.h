@@ -81,6 +81,8 @@ uint64_t qb200_launch_count(const qb200_ctx* ctx);
  *                    accumulation-bias compensation term; 5,6 with a cp.async staging ring
  *   tc_low k         replace the per-layout G=4 tensor-core rule by: lowest non-zero target >= k
  *   tcx 0            keep G=6 gates and G=4..6 expectation values on the FFMA2 kernels
+ *   mono 0           dense kernels also for XOR-monomial operators (Pauli strings) in qb200_expectation_value
+ *   expect_ug 2/3    several groups per thread per iteration in the G<=2 expectation kernel (slower; measured)
  *   tc_comp6 v       compensation constant of the G=6 tensor-core gate in units of 1e-9 (default 276)
  * Unknown keys return QB200_ERR_INVALID.  See DESIGN.md section 3. */
 int qb200_ctx_set_tuning(qb200_ctx* ctx, const char* key, int value);
@@ -119,7 +121,9 @@ int qb200_apply_controlled_gate(qb200_ctx* ctx, int dtype, void* state, unsigned
                                 const unsigned* cqs, unsigned num_controls, uint64_t cvals,
                                 const void* matrix);
 /* SimulatorCUDA::ExpectationValue (:216-260): <psi|M|psi>, num_targets in [1,6],
- * products in the state's precision, accumulation in double.  Synchronises. */
+ * products in the state's precision, accumulation in double.  Synchronises.
+ * Matrices with one non-zero per row in column r ^ const (Pauli strings, products of phase gates) on 3..6
+ * targets are evaluated as a single read pass without the mat-vec (csrc/expect_monomial.cu). */
 int qb200_expectation_value(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits,
                             const unsigned* qs, unsigned num_targets, const void* matrix,
                             double out_re_im[2]);

@@ -40,6 +40,8 @@ struct Tuning {
   int tc_low = -1;         // -1: per-layout rule (gate_launch.cuh); k >= 0: G=4 on the tensor cores iff lowest non-zero target >= k
   int expect_ug = -1;      // fp32 G<=2 expectation values (k_expect_stream): -1/1 = one group per thread per iteration;
                            // 2 = several groups, grid-strided; 3 = several groups, contiguous per block (both slower)
+  int mono = -1;           // -1 auto: G >= 3 expectation values of XOR-monomial matrices (Pauli strings) as a read pass
+                           // without a mat-vec (expect_monomial.cu); 0 = always the dense kernels
   int big = -1;            // -1 auto (on); 0 = fp32 G>=5 through the register/generic kernels;
                            // 1/2/3 = alternative launch shapes of k_gate_big (tools/microbench.py)
 };

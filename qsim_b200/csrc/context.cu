@@ -231,6 +231,7 @@ int qb200_ctx_set_tuning(qb200_ctx* ctx, const char* key, int value) {
   else if (!std::strcmp(key, "prefetch")) ctx->tune.prefetch = value;
   else if (!std::strcmp(key, "big")) ctx->tune.big = value;
   else if (!std::strcmp(key, "expect_ug")) ctx->tune.expect_ug = value;
+  else if (!std::strcmp(key, "mono")) ctx->tune.mono = value;
   else if (!std::strcmp(key, "tc")) ctx->tune.tc = value;
   else if (!std::strcmp(key, "tc_low")) ctx->tune.tc_low = value;
   else if (!std::strcmp(key, "tcx")) ctx->tune.tcx = value;

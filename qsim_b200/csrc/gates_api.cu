@@ -10,6 +10,11 @@ QB_DECL(gate_apply_f64, double)
 QB_DECL(gate_expect_f32, float)
 QB_DECL(gate_expect_f64, double)
 #undef QB_DECL
+// expect_monomial.cu: QB200_ERR_UNSUPPORTED = not an XOR-monomial matrix, take the dense kernels
+int expect_monomial_f32(qb200_ctx* ctx, const float* st, unsigned n, const unsigned* qs, unsigned nq, const float* m,
+                        double* out);
+int expect_monomial_f64(qb200_ctx* ctx, const double* st, unsigned n, const unsigned* qs, unsigned nq, const double* m,
+                        double* out);
 }  // namespace qb200
 
 using namespace qb200;
@@ -44,6 +49,15 @@ int qb200_expectation_value(qb200_ctx* ctx, int dtype, const void* state, unsign
   if (!out_re_im) return QB200_ERR_INVALID;
   out_re_im[0] = out_re_im[1] = 0;  // the reference returns 0 for unsupported sizes (:259)
   if (num_targets > kMaxTargets) return QB200_ERR_UNSUPPORTED;
+  // Pauli strings and other XOR-monomial operators: a read pass without a mat-vec (expect_monomial.cu).  G <= 2
+  // stays on k_expect_stream, which is at the read roofline already.
+  if (ctx && num_targets >= 3 && ctx->tune.mono != 0 && (dtype == QB200_F32 || dtype == QB200_F64)) {
+    const int rc = dtype == QB200_F32
+        ? expect_monomial_f32(ctx, (const float*) state, num_qubits, qs, num_targets, (const float*) matrix, out_re_im)
+        : expect_monomial_f64(ctx, (const double*) state, num_qubits, qs, num_targets, (const double*) matrix, out_re_im);
+    if (rc != QB200_ERR_UNSUPPORTED) return rc;
+    out_re_im[0] = out_re_im[1] = 0;
+  }
   if (dtype == QB200_F32)
     return gate_expect_f32(ctx, (float*) state, num_qubits, qs, num_targets, nullptr, 0, 0,
                            (const float*) matrix, out_re_im);

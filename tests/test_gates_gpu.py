@@ -186,6 +186,56 @@ def test_one_qubit_moments(oracle, cdt, n):
     assert np.array_equal(sim.OneQubitMoments(st), got)  # deterministic
 
 
+_PAULI = {
+    "I": np.eye(2), "X": np.array([[0, 1], [1, 0]]), "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.diag([1, -1]),
+    "S": np.diag([1, 1j]), "T": np.diag([1, np.exp(0.25j * np.pi)]), "P0": np.diag([1, 0]),  # projector: zero row
+    "XS": np.array([[0, 1], [1j, 0]]), "H": np.array([[1, 1], [1, -1]]) / np.sqrt(2),        # H: not monomial
+}
+
+
+def _string_matrix(names, weight, cdt):
+    """kron with names[k] on matrix-index bit k <-> qs[k] (lib/matrix.h:26-33)."""
+    m = np.array([[weight]], dtype=np.complex128)
+    for name in names:
+        m = np.kron(_PAULI[name], m)
+    return m.astype(cdt)
+
+
+@pytest.mark.parametrize("cdt", [np.complex64, np.complex128])
+@pytest.mark.parametrize("n", [6, 9, 14, 18])
+def test_pauli_string_expectation_read_pass(oracle, cdt, n):
+    """XOR-monomial operators (Pauli strings, phase gates, projectors) on 3..6 targets take the read pass of
+    csrc/expect_monomial.cu; it must agree with the oracle (lib/simulator_basic.h:296-342) and with the dense
+    kernels (tuning mono = 0), and anything with a Hadamard in it must fall through to the dense kernels."""
+    ss, sim = backends(cdt)
+    _, dense = backends(cdt)
+    dense.set_tuning("mono", 0)
+    host = random_state(n, cdt, seed=70 + n)
+    st = ss.Create(n)
+    ss.from_numpy(host, st)
+    rng = np.random.default_rng(n)
+    tol = 1e-6 if cdt == np.complex64 else 1e-13
+    cases = [(list("XYZ"), None), (list("ZZZ"), None), (list("IIII"), None), (list("XZYXZY"), None),
+             (list("ZZZZZZ"), None), (list("YYYYY"), None), (list("SXTZ"), None), (["P0", "X", "Z"], None),
+             (["XS", "XS", "Y"], None), (list("XHZ"), None), (list("ZZHZZZ"), None),
+             (list("XXX"), [0, 1, 2]), (list("XZYXZY"), list(range(6))), (list("YZX"), [n - 3, n - 2, n - 1]),
+             (list("IZX"), [0, 3, n - 1])]
+    for names, qs in cases:
+        g = len(names)
+        if qs is None:
+            qs = sorted(rng.choice(n, size=g, replace=False).tolist())
+        assert len(qs) == g
+        m = _string_matrix(names, 0.7 - 0.4j, cdt)
+        got = sim.ExpectationValue(qs, m, st)
+        want = oracle.expectation_value(host, qs, m)
+        assert abs(got - want) <= tol, (names, qs, got, want)
+        assert abs(got - dense.ExpectationValue(qs, m, st)) <= 2 * tol, (names, qs)
+    # batched: the read pass fills result slots like every other reduction
+    terms = [(list(range(6)), _string_matrix(list("XZYXZY"), 1.0, cdt)), ([1, 2, 4], _string_matrix(list("ZZZ"), 1.0, cdt))]
+    assert sim.ExpectationValues(terms, st) == [sim.ExpectationValue(q, m, st) for q, m in terms]
+    assert np.array_equal(ss.to_numpy(st), host)
+
+
 def test_gate_application_is_deterministic():
     """EXPECT_EQ bit-identical amplitudes across repeated runs
     (tests/simulator_testfixture.h:735-764)."""

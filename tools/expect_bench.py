@@ -57,6 +57,27 @@ for qs in cases:
     assert vb[-1] == v
     print(json.dumps({"n": n, "tune": args.tune, "expect": qs, "ms_per_call": round(single, 4), "GBps": round(read_bytes / single / 1e6),
                       "ms_batched": round(batch, 4), "GBps_batched": round(read_bytes / batch / 1e6)}), flush=True)
+# Pauli strings (XOR-monomial matrices): the read pass of csrc/expect_monomial.cu against the dense kernels (mono=0)
+PAULI = {"X": np.array([[0, 1], [1, 0]]), "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.diag([1, -1])}
+dense = qsim_b200.SimulatorB200(np.float32)
+dense.set_tuning("mono", 0)
+if not args.small:
+    for names, qs in (("XZY", [2, 5, 11]), ("XZYX", [8, 9, 14, 15]), ("ZZZZZ", [0, 3, 7, 12, 20]),
+                      ("XZYXZY", [0, 1, 2, 3, 4, 5]), ("XZYXZY", [1, 5, 9, 13, 17, 21]), ("XZYXZY", [n - 6 + k for k in range(6)])):
+        m = np.array([[1.0]])
+        for c in names:
+            m = np.kron(PAULI[c], m)
+        m = m.astype(np.complex64)
+        rec = {"n": n, "pauli": names, "qs": qs}
+        for label, s_ in (("read_pass", sim), ("dense", dense)):
+            terms = [(qs, m)] * args.reps
+            s_.ExpectationValues(terms[:3], st)
+            t0 = time.perf_counter()
+            s_.ExpectationValues(terms, st)
+            ms = (time.perf_counter() - t0) / args.reps * 1e3
+            rec[f"ms_batched_{label}"] = round(ms, 4)
+            rec[f"GBps_{label}"] = round(read_bytes / ms / 1e6)
+        print(json.dumps(rec), flush=True)
 for _ in range(3):
     ss.Norm(st)
 t0 = time.perf_counter()
