@@ -26,6 +26,14 @@ for rdt, cdt in ((np.float32, np.complex64), (np.float64, np.complex128)):
     # batched reductions (mapped pinned result slots) and the all-qubit moments kernel (3 passes at n = 15 / 14)
     terms = [(qs, unitary(len(qs), 3, cdt)) for qs in ([2], [0, 9], [1, 5, 9, 13, 14], [0, 1, 5, 9, 11, 14])] * 20
     vals = sim.ExpectationValues(terms, st)
+    # XOR-monomial operators (expect_monomial.cu): diagonal, in-pair swap, general; bit 0 in and out of the mask
+    P = {"X": np.array([[0, 1], [1, 0]]), "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.diag([1, -1])}
+    for names, qs in (("ZZZ", [0, 5, 14]), ("XZZ", [0, 5, 14]), ("XZYXZY", [0, 1, 2, 3, 4, 5]), ("ZXY", [3, 9, 14]),
+                      ("YYYYY", [1, 2, 6, 10, 13])):
+        m = np.array([[1.0]])
+        for c in names:
+            m = np.kron(P[c], m)
+        sim.ExpectationValue(qs, m.astype(cdt), st)
     mom = sim.OneQubitMoments(st)
     st13 = ss.Create(13); ss.SetStateUniform(st13)
     mom13 = sim.OneQubitMoments(st13)
