@@ -16,10 +16,12 @@
 // here: depolarizing noise after every gate qubit; observables = X_q and Z_q on every qubit
 // plus one 6-qubit Pauli string per window of 6 qubits.
 //
-//   [CUDA_VISIBLE_DEVICES=r] qsim_qtrajectory_b200 -c circuit -d maxtime -p 0.001 -0 traj0 -n num -f 4 [-v 0] [-b 1]
+//   [CUDA_VISIBLE_DEVICES=r] qsim_qtrajectory_b200 -c circuit -d maxtime -p 0.001 -0 traj0 -n num -f 4 [-v 0] [-b 2] [-j 1]
 // prints one JSON line: {"n":..,"traj0":..,"num":..,"seconds":..,"sums":[re,im,...]}
 #include <unistd.h>
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <complex>
@@ -27,7 +29,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <limits>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "circuit.h"
@@ -61,12 +65,16 @@ struct Options {
   // operators from the reduced density matrices, the rest batched, one stream synchronisation); 1: batched
   // only (same kernels and values as 0); 0: the reference's lib/expect.h, one synchronisation per string
   unsigned batch = 2;
+  // worker threads of this process, each with its own state, simulator and CUDA per-thread stream, over
+  // contiguous sub-slices of the repetition ids: one worker's host phases (fusing, Kraus sampling, reading
+  // results) overlap the other's kernels.  B200 backend only.
+  unsigned workers = 1;
 };
 
 Options Parse(int argc, char* argv[]) {
   Options o;
   int k;
-  while ((k = getopt(argc, argv, "c:d:p:0:n:f:t:v:b:")) != -1) {
+  while ((k = getopt(argc, argv, "c:d:p:0:n:f:t:v:b:j:")) != -1) {
     switch (k) {
       case 'c': o.circuit_file = optarg; break;
       case 'd': o.maxtime = std::atoi(optarg); break;
@@ -77,9 +85,10 @@ Options Parse(int argc, char* argv[]) {
       case 't': o.threads = std::atoi(optarg); break;
       case 'v': o.verbosity = std::atoi(optarg); break;
       case 'b': o.batch = std::atoi(optarg); break;
+      case 'j': o.workers = std::max(1, std::atoi(optarg)); break;
       default:
         std::fprintf(stderr, "usage: %s -c circuit [-d maxtime] [-p prob] [-0 traj0] [-n num] "
-                             "[-f max_fused_size] [-t threads] [-v verbosity] [-b batch]\n", argv[0]);
+                             "[-f max_fused_size] [-t threads] [-v verbosity] [-b batch] [-j workers]\n", argv[0]);
         std::exit(1);
     }
   }
@@ -110,7 +119,7 @@ std::vector<std::vector<qsim::OpString<FP>>> Observables(unsigned n) {
 // Counts the passes the drivers issue (algorithmic HBM bytes of the run):
 // gate pass = 16 * 2^n B, expectation pass = 8 * 2^n B in fp32.
 struct PassCount { uint64_t gates = 0, expects = 0, moment_calls = 0; };
-PassCount g_passes;
+thread_local PassCount g_passes;  // per worker, added up at the end
 
 template <typename Base>
 struct Counting {
@@ -188,53 +197,96 @@ int main(int argc, char* argv[]) {
   const auto ncircuit = MakeNoisy(circuit, Cirq::DepolarizingChannel<fp_type>(opt.p));
   const auto observables = Observables<fp_type>(circuit.num_qubits);
 
-  Simulator simulator = factory.CreateSimulator();
-  StateSpace state_space = factory.CreateStateSpace();
-  auto state = state_space.Create(circuit.num_qubits);
-  if (state_space.IsNull(state)) {
-    std::fprintf(stderr, "not enough memory\n");
-    return 1;
-  }
-
   typename QTSimulator::Parameter param;
   param.max_fused_size = opt.max_fused_size;
   param.verbosity = opt.verbosity;
   param.apply_last_deferred_ops = true;
 
+#ifdef QTRAJ_REFERENCE_CPU
+  const unsigned workers = 1;
+#else
+  const unsigned workers = std::max(1u, std::min(opt.workers, std::max(1u, opt.num)));
+#endif
+  using Clock = std::chrono::steady_clock;
   std::vector<std::complex<double>> sums(observables.size(), 0.0);
-  typename QTSimulator::Stat stat;
+  PassCount passes;
+  Clock::time_point first_start = Clock::time_point::max(), last_end = Clock::time_point::min();
+  std::mutex merge;
+  std::atomic<unsigned> ready{0};
+  std::atomic<bool> failed{false};
 
-  // one untimed trajectory: context creation, kernel loading, scratch growth
-  state_space.SetStateZero(state);
-  if (!QTSimulator::RunOnce(param, ncircuit, opt.traj0, state_space, simulator, state, stat)) return 1;
-  (void) ExpectationValue<IO, Fuser>(observables.back(), simulator, state);
-
-  g_passes = PassCount{};
-  const auto t0 = std::chrono::steady_clock::now();
-  for (unsigned i = 0; i < opt.num; ++i) {
-    state_space.SetStateZero(state);
-    // seed = repetition id, as QuantumTrajectorySimulator::RunBatch does (lib/qtrajectory.h:268)
-    if (!QTSimulator::RunOnce(param, ncircuit, uint64_t{opt.traj0} + i, state_space, simulator, state, stat)) {
-      return 1;
-    }
+  auto work = [&](unsigned w) {
+    // contiguous sub-slice of [traj0, traj0 + num)
+    const unsigned base = opt.num / workers, extra = opt.num % workers;
+    const unsigned first = opt.traj0 + w * base + std::min(w, extra), count = base + (w < extra ? 1 : 0);
+    Simulator simulator = factory.CreateSimulator();
+    StateSpace state_space = factory.CreateStateSpace();
 #ifndef QTRAJ_REFERENCE_CPU
-    if (opt.batch) {
-      const auto evals = ExpectationValues<IO, Fuser>(observables, simulator, state, opt.batch >= 2);
-      for (std::size_t k = 0; k < observables.size(); ++k) sums[k] += evals[k];
-      continue;
+    if (workers > 1) {  // CUDA's per-thread default stream: the workers' kernels interleave on the GPU
+      simulator.base.SetStream(qsim::b200::kStreamPerThread);
+      state_space.SetStream(qsim::b200::kStreamPerThread);
     }
 #endif
-    for (std::size_t k = 0; k < observables.size(); ++k) {
-      sums[k] += ExpectationValue<IO, Fuser>(observables[k], simulator, state);
+    auto state = state_space.Create(circuit.num_qubits);
+    bool ok = !state_space.IsNull(state);
+    if (!ok) std::fprintf(stderr, "not enough memory\n");
+    typename QTSimulator::Stat stat;
+    std::vector<std::complex<double>> local(observables.size(), 0.0);
+    if (ok) {
+      // one untimed trajectory: context creation, kernel loading, scratch growth
+      state_space.SetStateZero(state);
+      ok = QTSimulator::RunOnce(param, ncircuit, first, state_space, simulator, state, stat);
+      if (ok) (void) ExpectationValue<IO, Fuser>(observables.back(), simulator, state);
     }
+    if (!ok) failed = true;
+    ++ready;
+    while (ready.load() < workers) std::this_thread::yield();  // all workers start their timed loops together
+    g_passes = PassCount{};
+    const auto t0 = Clock::now();
+    for (unsigned i = 0; i < count && !failed.load(); ++i) {
+      state_space.SetStateZero(state);
+      // seed = repetition id, as QuantumTrajectorySimulator::RunBatch does (lib/qtrajectory.h:268)
+      if (!QTSimulator::RunOnce(param, ncircuit, uint64_t{first} + i, state_space, simulator, state, stat)) {
+        failed = true;
+        break;
+      }
+#ifndef QTRAJ_REFERENCE_CPU
+      if (opt.batch) {
+        const auto evals = ExpectationValues<IO, Fuser>(observables, simulator, state, opt.batch >= 2);
+        for (std::size_t k = 0; k < observables.size(); ++k) local[k] += evals[k];
+        continue;
+      }
+#endif
+      for (std::size_t k = 0; k < observables.size(); ++k) {
+        local[k] += ExpectationValue<IO, Fuser>(observables[k], simulator, state);
+      }
+    }
+    const auto t1 = Clock::now();
+    std::lock_guard<std::mutex> lock(merge);
+    for (std::size_t k = 0; k < sums.size(); ++k) sums[k] += local[k];
+    passes.gates += g_passes.gates;
+    passes.expects += g_passes.expects;
+    passes.moment_calls += g_passes.moment_calls;
+    first_start = std::min(first_start, t0);
+    last_end = std::max(last_end, t1);
+  };
+
+  if (workers == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (unsigned w = 0; w < workers; ++w) pool.emplace_back(work, w);
+    for (auto& t : pool) t.join();
   }
-  const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (failed) return 1;
+  const double seconds = std::chrono::duration<double>(last_end - first_start).count();
 
   std::printf("{\"n\": %u, \"traj0\": %u, \"num\": %u, \"num_ops\": %zu, \"num_observables\": %zu, "
-              "\"gate_passes\": %llu, \"expect_passes\": %llu, \"moment_calls\": %llu, \"seconds\": %.6f, \"sums\": [",
+              "\"gate_passes\": %llu, \"expect_passes\": %llu, \"moment_calls\": %llu, \"workers\": %u, "
+              "\"seconds\": %.6f, \"sums\": [",
               circuit.num_qubits, opt.traj0, opt.num, ncircuit.ops.size(), observables.size(),
-              (unsigned long long) g_passes.gates, (unsigned long long) g_passes.expects,
-              (unsigned long long) g_passes.moment_calls, seconds);
+              (unsigned long long) passes.gates, (unsigned long long) passes.expects,
+              (unsigned long long) passes.moment_calls, workers, seconds);
   for (std::size_t k = 0; k < sums.size(); ++k) {
     std::printf("%s%.9g, %.9g", k ? ", " : "", sums[k].real(), sums[k].imag());
   }

@@ -34,6 +34,10 @@ inline void Check(int status, const qb200_ctx* ctx, const char* file, int line) 
 }
 #define QB200_CHECK(ctx, call) ::qsim::b200::Check((call), (ctx), __FILE__, __LINE__)
 
+// SetStream(kStreamPerThread): CUDA's per-thread default stream (cudaStreamPerThread) -- every host thread gets its
+// own stream without creating one; what the multi-worker trajectory app uses (apps/qsim_qtrajectory_b200.cc -j).
+static void* const kStreamPerThread = reinterpret_cast<void*>(0x2);
+
 // One context per backend object; copies of the object share it.
 inline std::shared_ptr<qb200_ctx> MakeContext(int device = -1) {
   qb200_ctx* ctx = nullptr;

@@ -81,3 +81,9 @@ def test_b200_trajectories_match_reference_cpu(circuit_file):
         assert serial["sums"] == batched["sums"]
         assert serial["expect_passes"] == batched["expect_passes"] == ref["expect_passes"]
         assert np.abs(np.array(got["sums"]) - np.array(serial["sums"])).max() < 16 * 2e-5
+        # "-j 3": three worker threads (own state, own CUDA per-thread stream) over sub-slices of the ids:
+        # same trajectories, sums added in a different order
+        threaded = traj_farm.run_farm(circuit_file, 0, 16, gpus=1, p=0.05, max_fused_size=fused,
+                                      extra_args=("-j", "3"))
+        assert threaded["gate_passes"] == got["gate_passes"] and threaded["num"] == 16
+        assert np.abs(np.array(threaded["sums"]) - np.array(got["sums"])).max() < 1e-9

@@ -29,6 +29,9 @@ ap.add_argument("--batch", type=int, default=2,
                 help="2: single-qubit observables from the reduced density matrices (csrc/moments.cu) + the rest in one "
                      "batch; 1: all observables of a trajectory in one batch (expect_b200.h, one stream synchronisation); "
                      "0: the reference's lib/expect.h loop, one synchronisation per operator string")
+ap.add_argument("--workers", type=int, default=2,
+                help="worker threads per process (own state + CUDA per-thread stream each): one worker's host phases "
+                     "overlap the other's kernels")
 args = ap.parse_args()
 
 with tempfile.NamedTemporaryFile("w", suffix=f"_rqc_q{args.n}", delete=False) as f:
@@ -36,7 +39,8 @@ with tempfile.NamedTemporaryFile("w", suffix=f"_rqc_q{args.n}", delete=False) as
     path = f.name
 ppg = args.procs_per_gpu
 res = run_farm(path, 0, args.num * args.gpus, gpus=args.gpus * ppg, p=args.p, max_fused_size=args.fused,
-               device_ids=[d for d in range(args.gpus) for _ in range(ppg)], extra_args=("-b", str(args.batch)))
+               device_ids=[d for d in range(args.gpus) for _ in range(ppg)], extra_args=("-b", str(args.batch), "-j", str(args.workers)))
+res["workers_per_gpu"] = args.workers
 res["batch"] = args.batch
 res["procs_per_gpu"] = ppg
 os.unlink(path)
