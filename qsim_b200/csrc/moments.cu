@@ -7,7 +7,7 @@
 // and any single-qubit operator M has  <psi|M|psi> = m00 S00 + m11 S11 + m01 S01 + m10 conj(S01).
 //
 // One pass = one set B of T tile bits (T = 12 fp32 / 11 fp64: a 32 KB tile): the low 4 index bits (128-byte
-// runs -> fully coalesced 128-bit loads) plus up to T - 4 further bit positions.  A block stages the 2^T
+// runs -> fully coalesced 128-bit loads) plus a window of T - 4 consecutive higher bit positions.  A block stages the 2^T
 // amplitudes whose other index bits equal the tile number in shared memory (next tile prefetched into
 // registers meanwhile); the measured tile bits are taken two at a time: a warp reads the four amplitudes of a
 // (k1, k2) quad once and feeds both qubits' pairs from registers (fp32: packed FFMA2 on the (re, im) pairs as
@@ -15,8 +15,8 @@
 // the lanes of a warp spread over the banks.  Products in FP, per-tile sums in FP, running sums in double (the
 // reference's precision contract, lib/simulator_basic.h:323-324), fixed reduction tree -> deterministic.
 // Pass 0 measures bits 0..T-1, every later pass T - 4 new qubits: 3 passes at 26 qubits, 4 at 30 -- against
-// one pass per operator.  Measured (profiles/r01_ncu_moments_summary.txt): 0.74 ms at 26 qubits, 11.9 ms at 30
-// = 9 read-pass equivalents; pass 0 is bound by issue slots + the tile barrier (6 groups on 8 warps), not HBM.
+// one pass per operator.  Measured (profiles/r01_ncu_moments_summary.txt): 0.63 ms at 26 qubits, 10.6 ms at 30
+// = 8 read-pass equivalents; pass 0 is bound by issue slots + the tile barrier (6 groups on 8 warps), not HBM.
 #include <algorithm>
 
 #include "gate_kernels.cuh"
@@ -27,7 +27,8 @@ constexpr int kMomNT = 256;
 constexpr int kMomMaxT = 12;
 
 struct MomGeom {
-  uint32_t T = 0;                // tile bits
+  uint32_t T = 0;                // tile bits: index bits [0, L) and the window [hs, hs + T - L)
+  uint32_t L = 0, hs = 0;
   uint32_t pos[kMomMaxT] = {};   // their positions in the amplitude index, ascending
   uint32_t nm = 0;               // measured tile bits in this pass
   uint32_t mk[kMomMaxT] = {};    // tile-bit number of each
@@ -41,8 +42,8 @@ struct MomGeom {
   uint32_t gm[6][2] = {};        // index into mk[] / partials, 0xffffffff = filler bit
 };
 
-template <typename FP, int TMAX>
-__global__ void __launch_bounds__(kMomNT, 2)
+template <typename FP, int TMAX, int MINB>
+__global__ void __launch_bounds__(kMomNT, MINB)
 k_moments(const FP* __restrict__ st, const __grid_constant__ MomGeom g, double* __restrict__ partials) {
   using V2 = typename Vec2<FP>::type;
   constexpr int V = 16 / (int) sizeof(V2);                // amplitudes per 128-bit access
@@ -52,34 +53,33 @@ k_moments(const FP* __restrict__ st, const __grid_constant__ MomGeom g, double* 
   const uint32_t tile_amps = 1u << g.T;
   const uint32_t nvec = tile_amps / V;
 
-  auto deposit = [&](uint32_t j) {
-    uint64_t o = 0;
-    for (uint32_t k = 0; k < g.T; ++k) o |= uint64_t((j >> k) & 1u) << g.pos[k];
-    return o;
-  };
+  // tile bit k <-> index bit k (k < L) or hs + k - L: two shifts instead of a loop over bit positions
+  const uint32_t lmask = (1u << g.L) - 1, d = g.hs - g.L;
+  auto deposit = [&](uint32_t j) { return uint64_t(j & lmask) | (uint64_t(j >> g.L) << g.hs); };
   auto tile_base = [&](uint64_t t) {
-    for (uint32_t k = 0; k < g.T; ++k) {
-      const uint64_t lo = t & ((uint64_t{1} << g.pos[k]) - 1);
-      t = ((t - lo) << 1) | lo;
-    }
-    return t;
+    return ((t >> d) << (g.hs + g.T - g.L)) | ((t & ((uint64_t{1} << d) - 1)) << g.L);
   };
-  uint64_t off[NLD];
-#pragma unroll
-  for (int r = 0; r < NLD; ++r) off[r] = deposit((tid + kMomNT * r) * V);
 
   uint4 buf[NLD];
   auto load = [&](uint64_t t) {
     const FP* base = st + 2 * tile_base(t);
 #pragma unroll
     for (int r = 0; r < NLD; ++r)
-      if (tid + kMomNT * r < nvec) buf[r] = *reinterpret_cast<const uint4*>(base + 2 * off[r]);
+      if (tid + kMomNT * r < nvec)
+        buf[r] = *reinterpret_cast<const uint4*>(base + 2 * deposit((tid + kMomNT * r) * V));
   };
 
   double acc[2][4] = {};
   const uint32_t grp = w / g.sf, part = w - grp * g.sf;
   const uint32_t gi = grp < g.ngroups ? grp : 0;
   const uint32_t b1 = 1u << g.gk[gi][0], b2 = 1u << g.gk[gi][1], lo1 = b1 - 1, lo2 = b2 - 1;
+  // quad number -> tile index with zeros at the two measured bits; stepping by 32 quads = adding expand2(32) with
+  // the held bits set so that carries run through them
+  auto expand2 = [&](uint32_t o) {
+    uint32_t j = ((o & ~lo1) << 1) | (o & lo1);
+    return ((j & ~lo2) << 1) | (j & lo2);
+  };
+  const uint32_t held = b1 | b2, step = expand2(32);
   uint64_t t = blockIdx.x;
   if (t < g.ntiles) load(t);
   for (; t < g.ntiles; t += gridDim.x) {
@@ -123,9 +123,8 @@ k_moments(const FP* __restrict__ st, const __grid_constant__ MomGeom g, double* 
           pa[x][2] = fma2(a0, a1, pa[x][2]);                 // (sum x0 x1, sum y0 y1)
           pa[x][3] = fma2(a0, pack2(a1y, a1x), pa[x][3]);    // (sum x0 y1, sum y0 x1)
         };
-        for (uint32_t o = part * per + lane; o < (part + 1) * per; o += 32) {
-          uint32_t j = ((o & ~lo1) << 1) | (o & lo1);
-          j = ((j & ~lo2) << 1) | (j & lo2);
+        uint32_t j = expand2(part * per + lane);
+        for (uint32_t o = part * per + lane; o < (part + 1) * per; o += 32, j = ((j | held) + step) & ~held) {
           const uint64_t a00 = s64[j], a01 = s64[j | b1], a10 = s64[j | b2], a11 = s64[j | b1 | b2];
           pair_acc(0, a00, a01);
           pair_acc(0, a10, a11);
@@ -148,9 +147,8 @@ k_moments(const FP* __restrict__ st, const __grid_constant__ MomGeom g, double* 
           pa[x][2] = fma(a0.x, a1.x, fma(a0.y, a1.y, pa[x][2]));
           pa[x][3] = fma(a0.x, a1.y, fma(-a0.y, a1.x, pa[x][3]));
         };
-        for (uint32_t o = part * per + lane; o < (part + 1) * per; o += 32) {
-          uint32_t j = ((o & ~lo1) << 1) | (o & lo1);
-          j = ((j & ~lo2) << 1) | (j & lo2);
+        uint32_t j = expand2(part * per + lane);
+        for (uint32_t o = part * per + lane; o < (part + 1) * per; o += 32, j = ((j | held) + step) & ~held) {
           const V2 a00 = s[j], a01 = s[j | b1], a10 = s[j | b2], a11 = s[j | b1 | b2];
           pair_acc(0, a00, a01);
           pair_acc(0, a10, a11);
@@ -213,12 +211,12 @@ k_moments_finish(const double* __restrict__ partials, uint32_t blocks, const __g
   out[4 * g.qubit[m] + c] = v;
 }
 
-template <typename FP, int TMAX>
+template <typename FP, int TMAX, int MINB>
 int one_qubit_moments(qb200_ctx* ctx, const FP* st, unsigned n, double* out) {
   if (n == 0) return QB200_OK;
   if (reinterpret_cast<uintptr_t>(st) & 15) return QB200_ERR_UNSUPPORTED;  // 128-bit loads
   const unsigned T = std::min<unsigned>(TMAX, n), L = std::min<unsigned>(4, T);
-  auto kern = k_moments<FP, TMAX>;
+  auto kern = k_moments<FP, TMAX, MINB>;
   static const int occ = [&] {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kMomNT, 0) != cudaSuccess || nb < 1) {
@@ -242,21 +240,18 @@ int one_qubit_moments(qb200_ctx* ctx, const FP* st, unsigned n, double* out) {
     MomGeom g;
     g.T = T;
     g.ntiles = ntiles;
-    bool in[kMaxQubits + 1] = {};
-    for (unsigned b = 0; b < L; ++b) in[b] = true;
-    unsigned have = L, fresh[kMomMaxT], nfresh = 0;
+    const unsigned W = T - L;
+    unsigned fresh[kMomMaxT], nfresh = 0;
+    g.L = L;
     if (next == 0) {
-      for (unsigned b = 0; b < T; ++b) { in[b] = true; fresh[nfresh++] = b; }
-      have = T;
+      g.hs = L;
+      for (unsigned b = 0; b < T; ++b) fresh[nfresh++] = b;
       next = T;
     } else {
-      while (have < T && next < n) { in[next] = true; fresh[nfresh++] = next++; ++have; }
-      for (unsigned b = L; have < T; ++b)  // fill the tile with already measured low bits
-        if (!in[b]) { in[b] = true; ++have; }
+      g.hs = std::min(next, n - W);  // the window slides down over measured bits when fewer than W qubits are left
+      while (nfresh < W && next < n) fresh[nfresh++] = next++;
     }
-    unsigned k = 0;
-    for (unsigned b = 0; b < n; ++b)
-      if (in[b]) g.pos[k++] = b;
+    for (unsigned k = 0; k < T; ++k) g.pos[k] = k < L ? k : g.hs + (k - L);
     g.nm = nfresh;
     for (unsigned i = 0; i < nfresh; ++i) {
       g.qubit[i] = fresh[i];
@@ -296,7 +291,8 @@ extern "C" int qb200_one_qubit_moments(qb200_ctx* ctx, int dtype, const void* st
                                        double* out) {
   if (!ctx || !state || !out || num_qubits > kMaxQubits) return QB200_ERR_INVALID;
   DeviceGuard guard(ctx);
-  if (dtype == QB200_F32) return one_qubit_moments<float, 12>(ctx, (const float*) state, num_qubits, out);
-  if (dtype == QB200_F64) return one_qubit_moments<double, 11>(ctx, (const double*) state, num_qubits, out);
+  // two resident blocks per SM (128 registers): three (80 registers, 128-184 B of spills) measured 7 % slower
+  if (dtype == QB200_F32) return one_qubit_moments<float, 12, 2>(ctx, (const float*) state, num_qubits, out);
+  if (dtype == QB200_F64) return one_qubit_moments<double, 11, 2>(ctx, (const double*) state, num_qubits, out);
   return QB200_ERR_INVALID;
 }
