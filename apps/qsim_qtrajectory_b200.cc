@@ -196,6 +196,10 @@ int main(int argc, char* argv[]) {
   }
   const auto ncircuit = MakeNoisy(circuit, Cirq::DepolarizingChannel<fp_type>(opt.p));
   const auto observables = Observables<fp_type>(circuit.num_qubits);
+#ifndef QTRAJ_REFERENCE_CPU
+  // the observables are the same for every trajectory: reduce their strings to (qubits, matrix) once
+  const auto plan = MakeObservablePlan<IO, MultiQubitGateFuser<IO>>(observables, circuit.num_qubits);
+#endif
 
   typename QTSimulator::Parameter param;
   param.max_fused_size = opt.max_fused_size;
@@ -252,7 +256,7 @@ int main(int argc, char* argv[]) {
       }
 #ifndef QTRAJ_REFERENCE_CPU
       if (opt.batch) {
-        const auto evals = ExpectationValues<IO, Fuser>(observables, simulator, state, opt.batch >= 2);
+        const auto evals = ExpectationValues(plan, simulator, state, opt.batch >= 2);
         for (std::size_t k = 0; k < observables.size(); ++k) local[k] += evals[k];
         continue;
       }

@@ -29,7 +29,7 @@ ap.add_argument("--batch", type=int, default=2,
                 help="2: single-qubit observables from the reduced density matrices (csrc/moments.cu) + the rest in one "
                      "batch; 1: all observables of a trajectory in one batch (expect_b200.h, one stream synchronisation); "
                      "0: the reference's lib/expect.h loop, one synchronisation per operator string")
-ap.add_argument("--workers", type=int, default=2,
+ap.add_argument("--workers", type=int, default=1,
                 help="worker threads per process (own state + CUDA per-thread stream each): one worker's host phases "
                      "overlap the other's kernels")
 args = ap.parse_args()
