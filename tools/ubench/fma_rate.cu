@@ -1,4 +1,5 @@
 // fma_rate.cu -- measures FFMA / FFMA2 issue rates on sm_100a (tools only).
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench/fma_rate tools/ubench/fma_rate.cu
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
