@@ -193,6 +193,9 @@ class B200Engine:
     def norm(self) -> float:
         return self.ss.Norm(self.state)
 
+    def expectation_value(self, qs, matrix) -> complex:
+        return self.sim.ExpectationValue(qs, matrix, self.state)
+
     def slice(self, start_scalar: int, count_scalar: int):
         return self.shard[start_scalar:start_scalar + count_scalar]
 
@@ -422,6 +425,34 @@ class ShardedSimulator:
             t = torch.tensor([v], dtype=torch.float64, device=getattr(self.engine, "device", "cpu"))
             self.dist.all_reduce(t)
             v = float(t.item())
+        return v
+
+    def make_local(self, qubits: Sequence[int]):
+        """Collective: one swap that brings every global qubit of `qubits` into the local part; the victims are
+        the local qubits outside `qubits` on the highest physical bits."""
+        qubits = list(qubits)
+        incoming = [q for q in qubits if self.pos[q] >= self.n_local]
+        if not incoming:
+            return
+        spare = sorted((q for q in range(self.n) if self.pos[q] < self.n_local and q not in qubits),
+                       key=lambda q: -self.pos[q])
+        if len(spare) < len(incoming):
+            raise ValueError("not enough local qubits outside the operator to swap with")
+        self.swap(spare[:len(incoming)], incoming)
+
+    def expectation_value(self, qs: Sequence[int], matrix) -> complex:
+        """<psi|M|psi> on a sharded state (SimulatorCUDA::ExpectationValue, lib/simulator_cuda.h:216-260): the
+        operator's qubits are made local if they are not (one exchange), every rank runs the
+        read-only pass on its shard and the P partial values are added.  Collective: every rank gets the value."""
+        qs = list(qs)
+        self.make_local(qs)
+        sorted_bits, m = reindex_matrix(matrix, [self.pos[q] for q in qs])
+        v = complex(self.engine.expectation_value(sorted_bits, m))
+        if self.dist is not None and self.world > 1:
+            import torch
+            t = torch.tensor([v.real, v.imag], dtype=torch.float64, device=getattr(self.engine, "device", "cpu"))
+            self.dist.all_reduce(t)
+            v = complex(t[0].item(), t[1].item())
         return v
 
     def locate(self, logical_index: int) -> Tuple[int, int]:

@@ -47,6 +47,9 @@ class OracleEngine:
     def norm(self):
         return self.orc.norm(self.np)
 
+    def expectation_value(self, qs, matrix):
+        return self.orc.expectation_value(self.np, qs, matrix)
+
     def slice(self, start, count):
         return self.shard[start:start + count]
 
@@ -119,6 +122,16 @@ def random_ops(n, count, seed, max_local):
     return ops
 
 
+def expectation_cases(n):
+    """(qubits, matrix) pairs: low / high (global after most plans) / mixed targets, 1 to 3 qubits."""
+    rng = np.random.RandomState(77)
+    out = []
+    for qs in ([0], [n - 1], [1, n - 2], [n - 2, n - 1], [0, 3, n - 1], [2, 4, 5]):
+        d = 1 << len(qs)
+        out.append((qs, (rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))).astype(np.complex64)))
+    return out
+
+
 def oracle_full(n, ops):
     from oracle.oracle import Oracle
     orc = Oracle()
@@ -145,9 +158,13 @@ def _worker(rank, world, port, n, ops, transfer_scalars, out_dir, p2p=False):
         plan = sim.run(ops)
         norm = sim.norm()
         amp5 = sim.get_ampl(5)
+        swaps, sent, lsp = sim.stats.swaps, sim.stats.bytes_sent, sim.stats.local_swap_passes
+        # expectation values on the sharded state (operators of expectation_cases(n)): targets that sit on rank
+        # bits are swapped in first, so the qubit map -- saved below -- may change, the logical state must not
+        evs = [sim.expectation_value(qs, m) for qs, m in expectation_cases(n)]
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), shard=eng.np, pos=np.array(sim.pos), norm=norm,
-                 amp5=np.array([amp5.real, amp5.imag]), swaps=sim.stats.swaps, nplan=len(plan),
-                 bytes_sent=sim.stats.bytes_sent, local_swap_passes=sim.stats.local_swap_passes)
+                 amp5=np.array([amp5.real, amp5.imag]), swaps=swaps, nplan=len(plan),
+                 bytes_sent=sent, local_swap_passes=lsp, evs=np.array(evs), swaps_after=sim.stats.swaps)
     finally:
         dist.destroy_process_group()
 
@@ -191,6 +208,19 @@ def test_sharded_random_circuit_matches_unsharded_oracle(world, tmp_path):
     a5 = res[0]["amp5"]
     assert abs(complex(a5[0], a5[1]) - want[5]) < 2e-6
     assert int(res[0]["swaps"]) >= 1 and int(res[0]["swaps"]) == int(res[0]["nplan"])
+    check_expectations(n, want, res)
+
+
+def check_expectations(n, want, res):
+    """every rank holds the same values, equal to the oracle's on the unsharded state; at least one operator
+    needed its qubits swapped in."""
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    ref = np.array([orc.expectation_value(want, qs, m) for qs, m in expectation_cases(n)])
+    for r in res:
+        assert np.abs(r["evs"] - ref).max() < 2e-5, (r["evs"], ref)
+        assert np.array_equal(r["evs"], res[0]["evs"])
+    assert int(res[0]["swaps_after"]) > int(res[0]["swaps"])
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -206,6 +236,7 @@ def test_sharded_peer_memory_swap_path(world, tmp_path):
     assert abs(float(res[0]["norm"]) - 1.0) < 1e-5
     assert int(res[0]["swaps"]) >= 2 and int(res[0]["swaps"]) == int(res[0]["nplan"])
     assert int(res[0]["local_swap_passes"]) >= 1  # random victims do land on the low bits
+    check_expectations(n, want, res)
 
 
 def test_sharded_rqc_trace_world2(tmp_path):

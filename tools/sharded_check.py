@@ -27,7 +27,18 @@ norm = sim.norm()
 rs = np.random.RandomState(0)
 idx = [0, 1, 2, 7] + rs.randint(0, 1 << n, 60).tolist()
 amps = [sim.get_ampl(i) for i in idx]
-ok, maxerr = True, 0.0
+# expectation values on the sharded state: Pauli strings (read pass) and dense operators, local and global qubits
+P = {"X": np.array([[0, 1], [1, 0]]), "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.diag([1, -1])}
+def pauli(names):
+    m = np.array([[1.0]])
+    for c in names:
+        m = np.kron(P[c], m)
+    return m.astype(np.complex64)
+ecases = [([0], pauli("X")), ([n - 1], pauli("Z")), ([1, n - 1], rs.standard_normal((4, 4)).astype(np.complex64)),
+          ([2, 9, n - 2, n - 1], pauli("XZYX")), ([0, 3, 7, 12, n - 3, n - 1], pauli("XZYXZY"))]
+swaps_run = sim.stats.swaps
+evs = [sim.expectation_value(qs, m) for qs, m in ecases]
+ok, maxerr, everr = True, 0.0, 0.0
 if rank == 0:
     ss, s1 = qsim_b200.StateSpaceB200(np.float32, device=local), qsim_b200.SimulatorB200(np.float32, device=local)
     st = ss.Create(n); ss.SetStateZero(st)
@@ -35,8 +46,11 @@ if rank == 0:
         s1.ApplyGate(op.qubits, op.matrix, st)
     for i, a in zip(idx, amps):
         maxerr = max(maxerr, abs(a - ss.GetAmpl(st, i)))
-    ok = maxerr < 1e-6 and abs(norm - 1) < 1e-4
-    print(json.dumps({"world": world, "n": n, "ops": len(ops), "swaps": sim.stats.swaps, "local_swap_passes": sim.stats.local_swap_passes,
+    for (qs, m), v in zip(ecases, evs):
+        everr = max(everr, abs(v - s1.ExpectationValue(qs, m, st)))
+    ok = maxerr < 1e-6 and abs(norm - 1) < 1e-4 and everr < 1e-5
+    print(json.dumps({"world": world, "n": n, "ops": len(ops), "swaps": swaps_run, "swaps_for_expectations": sim.stats.swaps - swaps_run,
+                      "max_abs_err_expectations": everr, "local_swap_passes": sim.stats.local_swap_passes,
                       "bytes_sent_per_rank": sim.stats.bytes_sent, "norm": norm, "max_abs_err_vs_single_gpu": maxerr, "ok": ok, "p2p": p2p,
                       "exchange_ms": sim.exchange_device_ms(), "final_global_qubits": sim.global_qubits()}))
 dist.barrier()
