@@ -70,6 +70,13 @@ int qb200_last_cuda_error(const qb200_ctx* ctx);
 const char* qb200_last_cuda_error_string(const qb200_ctx* ctx);
 /* Number of kernels this context has launched (bench.py's gpu_launches). */
 uint64_t qb200_launch_count(const qb200_ctx* ctx);
+/* Name of the gate / expectation kernel the dispatcher chose for the LAST pass of this context ("k_gate_tca<4>",
+ * "k_gate_tile<4>", "k_gate_reg<2>", ...): bench.py labels its per-kernel roofline with it instead of
+ * re-stating the dispatch rule.  Static storage; "" before the first pass. */
+const char* qb200_last_kernel_name(const qb200_ctx* ctx);
+/* Persistent grids of this context are sized for `sms` SMs instead of all 148 (0 = all): used while an
+ * exchange kernel of a sharded state owns the remaining SMs (csrc/sharded.cu). */
+int qb200_ctx_set_sm_limit(qb200_ctx* ctx, int sms);
 /* Kernel-selection overrides for experiments and for the cross-check tests (defaults = -1 = auto):
  *   gate_mode 0      one amplitude per access in the register kernels
  *   force_generic 1  runtime-generic kernel for everything
@@ -93,8 +100,12 @@ int qb200_timer_stop_ms(qb200_ctx* ctx, float* ms);
 /* ---- VectorSpace (lib/vectorspace_cuda.h:43-167) ------------------------ */
 /* StateSpaceCUDA::MinSize (lib/statespace_cuda.h:81-83): scalars per state. */
 uint64_t qb200_min_size(unsigned num_qubits);
-/* VectorSpaceCUDA::Create(n) (:87-96).  QB200_ERR_OOM on failure. */
+/* VectorSpaceCUDA::Create(n) (:87-96).  QB200_ERR_OOM on failure.  The reference's Create is static and
+ * allocates on the CURRENT device; qb200_state_alloc keeps that meaning, qb200_state_alloc_on allocates on the
+ * context's device (what a caller driving several GPUs from one process wants).  Kernels of a context refuse a
+ * state that lives on another GPU (QB200_ERR_INVALID). */
 int qb200_state_alloc(unsigned num_qubits, int dtype, void** state);
+int qb200_state_alloc_on(qb200_ctx* ctx, unsigned num_qubits, int dtype, void** state);
 /* detail::free (:31-33) */
 int qb200_state_free(void* state);
 /* Copy state->state / state->host / host->state (:112-160).  `count` is in
@@ -134,7 +145,9 @@ int qb200_expectation_value(qb200_ctx* ctx, int dtype, const void* state, unsign
  * returns at once with its `out` set to NaN; its result goes to the next slot of a mapped
  * pinned host array.  `end` synchronises once and copies the `*count` results, (re, im) per
  * slot in call order, to `out` (capacity in slots; QB200_ERR_INVALID if it is too small).
- * `expected` only pre-sizes the slot array; it grows on demand. */
+ * `expected` only pre-sizes the slot array; it grows on demand.  An operator on more than 6 qubits takes a
+ * slot holding 0 (the reference's answer for it), so results pair with calls by position.  qb200_collapse
+ * needs its norm on the host at once and returns QB200_ERR_INVALID inside a batch. */
 /* Reduced density matrices of ALL qubits in a handful of read-only passes (3 at 26 qubits, 4 at 30) instead
  * of one pass per single-qubit operator (no reference counterpart; csrc/moments.cu).  out[4q .. 4q+3] =
  * S00, S11, Re S01, Im S01 of qubit q with S00 / S11 = sum |a_i|^2 over bit_q(i) = 0 / 1 and
@@ -184,6 +197,12 @@ int qb200_find_measured_bits(qb200_ctx* ctx, int dtype, const void* state, unsig
  * the rest by 1/sqrt(masked norm).  out_norm (may be NULL) receives that norm. */
 int qb200_collapse(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits,
                    uint64_t mask, uint64_t bits, double* out_norm);
+/* The two halves of Collapse, for callers that combine several shards (csrc/sharded.cu): sum |amp|^2 over
+ * (i & mask) == bits, and "zero where (i & mask) != bits, scale the rest by renorm". */
+int qb200_masked_norm(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits,
+                      uint64_t mask, uint64_t bits, double* out);
+int qb200_collapse_scaled(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits,
+                          uint64_t mask, uint64_t bits, double renorm);
 /* InternalToNormalOrder / NormalToInternalOrder (:85-107): identity here. */
 int qb200_internal_to_normal_order(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits);
 int qb200_normal_to_internal_order(qb200_ctx* ctx, int dtype, void* state, unsigned num_qubits);
@@ -211,6 +230,114 @@ int qb200_ipc_close(void* peer_state);
 int qb200_swap_global_local(qb200_ctx* ctx, int dtype, void* state, unsigned num_local_qubits,
                             void* const* peer_states, unsigned k, const unsigned* local_bits,
                             unsigned my_value);
+
+
+/* ---- sharded states behind the same operations (csrc/sharded.cu) ----------------------------------------
+ * qb200_sv = one state of n qubits over 2^g shards + its qubit map + one context/stream per local shard: the
+ * counterpart of the multi-device State of lib/vectorspace_custatevecex.h:189-287,385-470 with its wire ordering
+ * (:163-177).  Qubit arguments are LOGICAL qubits; the library tracks where each one lives.  Gates may touch any
+ * qubits as long as the targets fit one shard (lib/simulator_custatevecex.h:67-71): a target on a global qubit
+ * triggers a local<->global exchange (online: least-recently-used victims; qb200_sv_run: planned over the whole
+ * gate list with reordering of commuting gates, csrc/sv_plan.h).  The exchange is one kernel per GPU that pushes
+ * amplitudes into the peers' memory over NVLink, bracketed by stream-ordered barriers; nothing on this path
+ * synchronises the host.  Reductions add per-shard results; Sample / PartialNorms / FindMeasuredBits / host
+ * copies first restore the canonical map (pos[q] = q) so they see the same amplitude order as an unsharded state.
+ *
+ * Ownership modes: qb200_sv_create -- this process drives every shard (devices[r] hosts shard r; a device may be
+ * named several times, which is how a one-GPU box exercises the exchange); qb200_sv_create_mp -- one process per
+ * shard, `comm` supplies the three host-side collectives (the role of custatevecExCommunicator,
+ * lib/multiprocess_custatevecex.h:82-87).  In mp mode every rank must make the same calls in the same order;
+ * values returned to the host are identical on all ranks. */
+typedef struct qb200_sv qb200_sv;
+
+typedef struct {
+  void* user;
+  /* recv = concatenation over ranks of each rank's `bytes` bytes at `send` (host memory); 0 on success */
+  int (*allgather)(void* user, const void* send, void* recv, uint64_t bytes);
+  /* in-place sum over ranks of `count` doubles (host memory); 0 on success */
+  int (*allreduce_sum_f64)(void* user, double* inout, uint64_t count);
+  int (*barrier)(void* user);
+} qb200_comm;
+
+/* One fused gate of a circuit: lib/gate.h Gate / FusedGate / ControlledGate as plain pointers.  qs sorted
+ * ascending, matrix as in qb200_apply_gate, bit i of cvals <-> i-th lowest control qubit. */
+typedef struct {
+  unsigned num_targets;
+  const unsigned* qs;
+  unsigned num_controls;
+  const unsigned* cqs;
+  uint64_t cvals;
+  const void* matrix;
+} qb200_gate;
+
+typedef struct {
+  uint64_t swaps;                /* exchanges so far */
+  uint64_t local_swap_passes;    /* 2-qubit SWAP passes (in-place exchange of low bits, canonicalisation) */
+  uint64_t gate_passes;
+  double bytes_sent_per_shard;   /* sum over exchanges of shard_bytes * (1 - 2^-k) */
+  double exchange_ms;            /* device time of the exchanges (CUDA events on the first local shard) */
+} qb200_sv_stats;
+
+int qb200_sv_create(const int* devices, unsigned num_shards, unsigned num_qubits, int dtype, qb200_sv** sv);
+int qb200_sv_create_mp(int device, unsigned rank, unsigned world, const qb200_comm* comm, unsigned num_qubits,
+                       int dtype, qb200_sv** sv);
+int qb200_sv_destroy(qb200_sv* sv);
+unsigned qb200_sv_num_qubits(const qb200_sv* sv);
+unsigned qb200_sv_num_shards(const qb200_sv* sv);
+unsigned qb200_sv_num_local_qubits(const qb200_sv* sv);
+unsigned qb200_sv_num_local_shards(const qb200_sv* sv);
+int qb200_sv_last_cuda_error(const qb200_sv* sv);
+/* pos[q] = physical index bit of logical qubit q (bits >= num_local_qubits are the shard number) */
+int qb200_sv_qubit_map(const qb200_sv* sv, unsigned* pos);
+/* the i-th shard this process owns: its number, device, current device buffer and context (any may be NULL) */
+int qb200_sv_shard(const qb200_sv* sv, unsigned local_index, unsigned* rank, int* device, void** state, qb200_ctx** ctx);
+/* keys: "swap_mode" (-1 auto: out of place when a second buffer fits, 0 in place, 1 out of place), "reorder"
+ * (1: qb200_sv_run may reorder commuting gates, 0: program order), "barrier_flags" (1: flag words in peer memory,
+ * 0: CUDA events -- single-process only); any other key is forwarded to qb200_ctx_set_tuning of every shard. */
+int qb200_sv_set_option(qb200_sv* sv, const char* key, int value);
+int qb200_sv_sync(qb200_sv* sv);
+uint64_t qb200_sv_launch_count(const qb200_sv* sv);
+int qb200_sv_get_stats(qb200_sv* sv, qb200_sv_stats* out);   /* synchronises */
+int qb200_sv_reset_stats(qb200_sv* sv);
+/* StateSpace members on a sharded state (lib/statespace_custatevecex.h:79-147, lib/statespace_cuda.h) */
+int qb200_sv_set_all_zeros(qb200_sv* sv);
+int qb200_sv_set_state_zero(qb200_sv* sv);
+int qb200_sv_set_state_uniform(qb200_sv* sv);
+int qb200_sv_reset_map(qb200_sv* sv);  /* identity map without moving data: only before (re)initialising the state */
+int qb200_sv_get_ampl(qb200_sv* sv, uint64_t i, double out_re_im[2]);
+int qb200_sv_set_ampl(qb200_sv* sv, uint64_t i, double re, double im);
+int qb200_sv_bulk_set_ampl(qb200_sv* sv, uint64_t mask, uint64_t bits, double re, double im, int exclude);
+int qb200_sv_norm(qb200_sv* sv, double* out);
+int qb200_sv_inner_product(qb200_sv* a, qb200_sv* b, double out_re_im[2]);  /* may re-map both states */
+int qb200_sv_add(qb200_sv* src, qb200_sv* dest);
+int qb200_sv_copy(qb200_sv* src, qb200_sv* dest);
+int qb200_sv_multiply(qb200_sv* sv, double a);
+int qb200_sv_sample(qb200_sv* sv, const double* sorted_rs, uint64_t num_samples, uint64_t* out);
+uint64_t qb200_sv_partial_norms_count(const qb200_sv* sv);
+int qb200_sv_partial_norms(qb200_sv* sv, double* out);
+int qb200_sv_find_measured_bits(qb200_sv* sv, uint64_t m, double r, uint64_t mask, uint64_t* out_bits);
+int qb200_sv_collapse(qb200_sv* sv, uint64_t mask, uint64_t bits, double* out_norm);
+/* whole state, normal order, host memory; a multi-process state moves only this process's shard (at its offset) */
+int qb200_sv_copy_to_host(qb200_sv* sv, void* host_dst);
+int qb200_sv_copy_from_host(qb200_sv* sv, const void* host_src);
+/* Simulator members (lib/simulator_custatevecex.h:60-196) */
+int qb200_sv_apply_gate(qb200_sv* sv, const unsigned* qs, unsigned num_targets, const void* matrix);
+int qb200_sv_apply_controlled_gate(qb200_sv* sv, const unsigned* qs, unsigned num_targets, const unsigned* cqs,
+                                   unsigned num_controls, uint64_t cvals, const void* matrix);
+int qb200_sv_expectation_value(qb200_sv* sv, const unsigned* qs, unsigned num_targets, const void* matrix,
+                               double out_re_im[2]);
+/* A whole fused circuit: plans the exchanges over the list (csrc/sv_plan.h) and applies it -- what
+ * custatevecExSVUpdaterEnqueueMatrix + Apply do for the reference (lib/run_custatevecex.h:243-305). */
+int qb200_sv_run(qb200_sv* sv, const qb200_gate* gates, uint64_t count);
+/* The planner alone (host only, no GPU needed): global_qubits = the num_global qubits that are global at the
+ * start (NULL: the top ones).  steps: a value >= 0 is the index of the gate to apply next; -k starts an exchange
+ * and is followed by its k victims (local -> global) and k incoming qubits (global -> local).  Call with
+ * steps = NULL to size the buffer (*num_steps). */
+int qb200_sv_plan(unsigned num_qubits, unsigned num_global, const qb200_gate* gates, uint64_t count,
+                  const unsigned* global_qubits, int reorder, int64_t* steps, uint64_t capacity, uint64_t* num_steps);
+/* explicit exchange of k local (victims) with k global (incoming) logical qubits; restoring pos[q] = q */
+int qb200_sv_swap(qb200_sv* sv, const unsigned* victims, const unsigned* incoming, unsigned k);
+int qb200_sv_canonicalize(qb200_sv* sv);
 
 #ifdef __cplusplus
 }

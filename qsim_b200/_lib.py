@@ -69,6 +69,75 @@ SIGNATURES = {
     "qb200_swap_global_local": (_i, [_vp, _i, _vp, _u, C.POINTER(_vp), _u, _pu, _u]),
 }
 
+
+class Comm(C.Structure):
+    """qb200_comm: host-side collectives for a multi-process sharded state."""
+    ALLGATHER = C.CFUNCTYPE(_i, _vp, _vp, _vp, _u64)
+    ALLREDUCE = C.CFUNCTYPE(_i, _vp, _pd, _u64)
+    BARRIER = C.CFUNCTYPE(_i, _vp)
+    _fields_ = [("user", _vp), ("allgather", ALLGATHER), ("allreduce_sum_f64", ALLREDUCE), ("barrier", BARRIER)]
+
+
+class Gate(C.Structure):
+    """qb200_gate"""
+    _fields_ = [("num_targets", _u), ("qs", _pu), ("num_controls", _u), ("cqs", _pu), ("cvals", _u64), ("matrix", _vp)]
+
+
+class SvStats(C.Structure):
+    """qb200_sv_stats"""
+    _fields_ = [("swaps", _u64), ("local_swap_passes", _u64), ("gate_passes", _u64),
+                ("bytes_sent_per_shard", _d), ("exchange_ms", _d)]
+
+
+SIGNATURES.update({
+    "qb200_state_alloc_on": (_i, [_vp, _u, _i, C.POINTER(_vp)]),
+    "qb200_last_kernel_name": (C.c_char_p, [_vp]),
+    "qb200_ctx_set_sm_limit": (_i, [_vp, _i]),
+    "qb200_masked_norm": (_i, [_vp, _i, _vp, _u, _u64, _u64, _pd]),
+    "qb200_collapse_scaled": (_i, [_vp, _i, _vp, _u, _u64, _u64, _d]),
+    "qb200_sv_create": (_i, [C.POINTER(_i), _u, _u, _i, C.POINTER(_vp)]),
+    "qb200_sv_create_mp": (_i, [_i, _u, _u, C.POINTER(Comm), _u, _i, C.POINTER(_vp)]),
+    "qb200_sv_destroy": (_i, [_vp]),
+    "qb200_sv_num_qubits": (_u, [_vp]),
+    "qb200_sv_num_shards": (_u, [_vp]),
+    "qb200_sv_num_local_qubits": (_u, [_vp]),
+    "qb200_sv_num_local_shards": (_u, [_vp]),
+    "qb200_sv_last_cuda_error": (_i, [_vp]),
+    "qb200_sv_qubit_map": (_i, [_vp, _pu]),
+    "qb200_sv_shard": (_i, [_vp, _u, _pu, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_vp)]),
+    "qb200_sv_set_option": (_i, [_vp, C.c_char_p, _i]),
+    "qb200_sv_sync": (_i, [_vp]),
+    "qb200_sv_launch_count": (_u64, [_vp]),
+    "qb200_sv_get_stats": (_i, [_vp, C.POINTER(SvStats)]),
+    "qb200_sv_reset_stats": (_i, [_vp]),
+    "qb200_sv_set_all_zeros": (_i, [_vp]),
+    "qb200_sv_set_state_zero": (_i, [_vp]),
+    "qb200_sv_set_state_uniform": (_i, [_vp]),
+    "qb200_sv_reset_map": (_i, [_vp]),
+    "qb200_sv_get_ampl": (_i, [_vp, _u64, _pd]),
+    "qb200_sv_set_ampl": (_i, [_vp, _u64, _d, _d]),
+    "qb200_sv_bulk_set_ampl": (_i, [_vp, _u64, _u64, _d, _d, _i]),
+    "qb200_sv_norm": (_i, [_vp, _pd]),
+    "qb200_sv_inner_product": (_i, [_vp, _vp, _pd]),
+    "qb200_sv_add": (_i, [_vp, _vp]),
+    "qb200_sv_copy": (_i, [_vp, _vp]),
+    "qb200_sv_multiply": (_i, [_vp, _d]),
+    "qb200_sv_sample": (_i, [_vp, _pd, _u64, _pu64]),
+    "qb200_sv_partial_norms_count": (_u64, [_vp]),
+    "qb200_sv_partial_norms": (_i, [_vp, _pd]),
+    "qb200_sv_find_measured_bits": (_i, [_vp, _u64, _d, _u64, _pu64]),
+    "qb200_sv_collapse": (_i, [_vp, _u64, _u64, _pd]),
+    "qb200_sv_copy_to_host": (_i, [_vp, _vp]),
+    "qb200_sv_copy_from_host": (_i, [_vp, _vp]),
+    "qb200_sv_apply_gate": (_i, [_vp, _pu, _u, _vp]),
+    "qb200_sv_apply_controlled_gate": (_i, [_vp, _pu, _u, _pu, _u, _u64, _vp]),
+    "qb200_sv_expectation_value": (_i, [_vp, _pu, _u, _vp, _pd]),
+    "qb200_sv_run": (_i, [_vp, C.POINTER(Gate), _u64]),
+    "qb200_sv_plan": (_i, [_u, _u, C.POINTER(Gate), _u64, _pu, _i, C.POINTER(C.c_int64), _u64, _pu64]),
+    "qb200_sv_swap": (_i, [_vp, _pu, _pu, _u]),
+    "qb200_sv_canonicalize": (_i, [_vp]),
+})
+
 _lib = None
 
 

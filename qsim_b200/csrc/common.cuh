@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 
@@ -63,6 +64,9 @@ struct qb200_ctx {
   int last_error = 0;             // cudaError_t
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_limit = 0;               // > 0: persistent grids are sized for this many SMs (a concurrent exchange kernel owns the rest)
+  const void* checked_ptr = nullptr;  // last state pointer verified to live on `device` (check_state_device)
+  const char* last_kernel = "";   // name of the gate kernel the dispatcher picked last (qb200_last_kernel_name)
   qb200::Tuning tune;
 };
 
@@ -89,10 +93,32 @@ inline int cuda_status(qb200_ctx* ctx, cudaError_t e) {
     if (e__ != cudaSuccess) return ::qb200::cuda_status((ctx), e__); \
   } while (0)
 
+// QB200_ERR_INVALID when `p` is plain device memory of ANOTHER GPU than the context's (kernels of this context would
+// reach it over the interconnect, or fault); one runtime query per new pointer, remembered in the context.
+int check_state_device(qb200_ctx* ctx, const void* p);
+
 // Lazily grown device scratch / pinned host slot.
 int ensure_scratch(qb200_ctx* ctx, size_t bytes);
 int ensure_pinned(qb200_ctx* ctx, size_t bytes);
 int ensure_dmat(qb200_ctx* ctx);
+
+// SMs a persistent grid may assume it owns.
+inline int grid_sms(const qb200_ctx* ctx) { return ctx->sm_limit > 0 && ctx->sm_limit < kNumSMs ? ctx->sm_limit : kNumSMs; }
+
+// Function attributes (dynamic shared memory opt-in) and occupancy answers are PER DEVICE: a launcher keeps one
+// of these as a function-local static and fills the slot of ctx->device on first use there (the caller holds a
+// DeviceGuard, so the current device is ctx->device).  Slots are idempotent, a race only repeats the query.
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+  std::atomic<int> v[kMaxDevices];
+  PerDevice() { for (auto& x : v) x.store(0, std::memory_order_relaxed); }
+  template <typename F> int get(const qb200_ctx* ctx, F&& init) {
+    const int d = ctx->device >= 0 && ctx->device < kMaxDevices ? ctx->device : 0;
+    int r = v[d].load(std::memory_order_acquire);
+    if (r == 0) { r = init(); v[d].store(r, std::memory_order_release); }
+    return r;
+  }
+};
 
 struct DeviceGuard {
   explicit DeviceGuard(const qb200_ctx* ctx) {

@@ -70,6 +70,18 @@ int ensure_dmat(qb200_ctx* ctx) {
   return QB200_OK;
 }
 
+int check_state_device(qb200_ctx* ctx, const void* p) {
+  if (p == ctx->checked_ptr) return QB200_OK;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return QB200_OK;  // not a CUDA pointer the runtime knows: the launch itself will report it
+  }
+  if (a.type == cudaMemoryTypeDevice && a.device != ctx->device) return QB200_ERR_INVALID;
+  ctx->checked_ptr = p;
+  return QB200_OK;
+}
+
 // Copies a host matrix into the next ring slot (pinned -> device, async) and
 // returns the device address.  The slot is recycled only after the kernel that
 // consumed it has finished (event recorded by stage_matrix_done).
@@ -151,13 +163,26 @@ int finish_expectation(qb200_ctx* ctx, double* partials, uint32_t blocks, double
   return QB200_OK;
 }
 
+// An unsupported operator inside a batch still takes a slot (value 0, what the reference's ExpectationValue
+// returns for it, lib/simulator_cuda.h:259), so that callers can pair results with calls by position.
+int batch_zero_slot(qb200_ctx* ctx) {
+  if (!ctx->batching) return QB200_OK;
+  DeviceGuard guard(ctx);
+  int rc = ensure_results(ctx, ctx->batch_count + 1);
+  if (rc) return rc;
+  ctx->res[2 * size_t{ctx->batch_count}] = 0;      // host write: no kernel owns this slot
+  ctx->res[2 * size_t{ctx->batch_count} + 1] = 0;
+  ++ctx->batch_count;
+  return QB200_OK;
+}
+
 }  // namespace qb200
 
 using namespace qb200;
 
 extern "C" {
 
-int qb200_abi_version(void) { return 1; }
+int qb200_abi_version(void) { return 2; }
 
 int qb200_device_count(int* count) {
   if (!count) return QB200_ERR_INVALID;
@@ -262,7 +287,7 @@ int qb200_timer_stop_ms(qb200_ctx* ctx, float* ms) {
 
 uint64_t qb200_min_size(unsigned num_qubits) { return uint64_t{2} << num_qubits; }
 
-int qb200_state_alloc(unsigned num_qubits, int dtype, void** state) {
+static int state_alloc(unsigned num_qubits, int dtype, void** state) {
   if (!state || num_qubits > kMaxQubits || (dtype != QB200_F32 && dtype != QB200_F64))
     return QB200_ERR_INVALID;
   *state = nullptr;
@@ -274,6 +299,22 @@ int qb200_state_alloc(unsigned num_qubits, int dtype, void** state) {
     *state = nullptr;
     return e == cudaErrorMemoryAllocation ? QB200_ERR_OOM : QB200_ERR_CUDA;
   }
+  return QB200_OK;
+}
+
+int qb200_state_alloc(unsigned num_qubits, int dtype, void** state) { return state_alloc(num_qubits, dtype, state); }
+
+int qb200_state_alloc_on(qb200_ctx* ctx, unsigned num_qubits, int dtype, void** state) {
+  if (!ctx) return QB200_ERR_INVALID;
+  DeviceGuard guard(ctx);
+  return state_alloc(num_qubits, dtype, state);
+}
+
+const char* qb200_last_kernel_name(const qb200_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
+
+int qb200_ctx_set_sm_limit(qb200_ctx* ctx, int sms) {
+  if (!ctx || sms < 0) return QB200_ERR_INVALID;
+  ctx->sm_limit = sms;
   return QB200_OK;
 }
 

@@ -93,7 +93,8 @@ template <int G, bool EXPECT>
 int launch_dbig(qb200_ctx* ctx, double* st, const Geom& g, const double* m, double* out) {
   auto kern = k_gate_dbig<G, EXPECT>;
   constexpr size_t smem = (size_t{2} << G) * kDThreads * sizeof(double);
-  static const int occ = [&] {
+  static PerDevice occ_cache;
+  const int occ = occ_cache.get(ctx, [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kDThreads, smem) != cudaSuccess || nb < 1) {
@@ -101,12 +102,12 @@ int launch_dbig(qb200_ctx* ctx, double* st, const Geom& g, const double* m, doub
       nb = 1;
     }
     return nb;
-  }();
+  });
   const void* dmat = nullptr;
   int rc = stage_matrix(ctx, m, sizeof(double) * (size_t{2} << (2 * G)), &dmat);
   if (rc) return rc;
   const uint64_t need = (g.work + kDThreads - 1) / kDThreads;
-  uint64_t persistent = uint64_t{kNumSMs} * occ;
+  uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
   if (EXPECT && persistent > kExpectMaxBlocks) persistent = kExpectMaxBlocks;
   const uint32_t blocks = (uint32_t) (need < persistent ? need : persistent);
   double* partials = nullptr;

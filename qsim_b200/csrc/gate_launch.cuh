@@ -55,7 +55,8 @@ template <int G, int MODE, int PNT, int PD, int PMINB>
 int launch_pipe(qb200_ctx* ctx, float* st, const Geom& g, const MatParam<float, G>& mat) {
   auto kern = k_gate_pipe<G, MODE, PNT, PD, PMINB>;
   constexpr size_t smem = pipe_smem_bytes<G, MODE, PNT, PD>();
-  static const int occ = [&] {
+  static PerDevice occ_cache;
+  const int occ = occ_cache.get(ctx, [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PNT, smem) != cudaSuccess || nb < 1) {
@@ -63,9 +64,9 @@ int launch_pipe(qb200_ctx* ctx, float* st, const Geom& g, const MatParam<float, 
       nb = 1;
     }
     return nb;
-  }();
+  });
   const uint64_t need = (g.work + PNT - 1) / PNT;
-  const uint64_t persistent = uint64_t{kNumSMs} * occ;
+  const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
   const uint32_t blocks = (uint32_t) (need < persistent ? need : persistent);
   kern<<<blocks, PNT, smem, ctx->stream>>>(st, g, mat);
   QB_LAUNCHED(ctx);
@@ -78,7 +79,8 @@ int launch_tile(qb200_ctx* ctx, float* st, const TileGeom& t, const float* m) {
   mat.fill(m);
   auto kern = k_gate_tile<G, PAIR, TNT, TD, TMINB>;
   constexpr size_t smem = tile_smem_bytes<G, TNT, TD>();
-  static const int occ = [&] {
+  static PerDevice occ_cache;
+  const int occ = occ_cache.get(ctx, [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TNT, smem) != cudaSuccess || nb < 1) {
@@ -86,10 +88,10 @@ int launch_tile(qb200_ctx* ctx, float* st, const TileGeom& t, const float* m) {
       nb = 1;
     }
     return nb;
-  }();
+  });
   constexpr int warps = TNT / 32;
   const uint64_t need = (t.work + warps - 1) / warps;
-  const uint64_t persistent = uint64_t{kNumSMs} * occ;
+  const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
   const uint32_t blocks = (uint32_t) (need < persistent ? need : persistent);
   kern<<<blocks, TNT, smem, ctx->stream>>>(st, t, mat);
   QB_LAUNCHED(ctx);
@@ -123,7 +125,7 @@ int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) 
         constexpr int kLoads = MODE == kV2T ? (1 << G) / 2 : (1 << G);  // per group
         constexpr int kUG = kLoads >= 4 ? 1 : 4 / kLoads;
         auto run = [&](auto kern, int occ, int ug, int contiguous) -> int {
-          const uint64_t persistent = uint64_t{kNumSMs} * occ;
+          const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
           const uint64_t need = (blocks64 + ug - 1) / ug;
           const uint32_t nb = (uint32_t) (need < persistent ? need : persistent);
           int rc = ensure_scratch(ctx, (2 * size_t{nb} + 2) * sizeof(double));
@@ -163,7 +165,7 @@ int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) 
       if (ctx->tune.prefetch != 0) {
         auto kern = k_gate_reg<FP, G, MODE, UNROLL, false, true, NT, MINB, Mat>;
         static const int occ = resident_blocks(kern, NT);
-        const uint64_t persistent = uint64_t{kNumSMs} * occ;
+        const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
         const uint32_t blocks = (uint32_t) (blocks64 < persistent ? blocks64 : persistent);
         kern<<<blocks, NT, 0, ctx->stream>>>(st, g, mat, nullptr);
         QB_LAUNCHED(ctx);
@@ -233,6 +235,7 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
   if (!ctx || !st || !m || (nq && !qs) || (nc && !cqs)) return QB200_ERR_INVALID;
   if (nq > kMaxTargets) return QB200_ERR_UNSUPPORTED;
   DeviceGuard guard(ctx);
+  if (int drc = check_state_device(ctx, st)) return drc;
 
   const bool aligned16 = (reinterpret_cast<uintptr_t>(st) & 15) == 0;
   bool generic = ctx->tune.force_generic || (int) nq > RegLimits<FP>::kMaxG ||
@@ -266,6 +269,8 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
       Geom tg;
       int trc = make_geom(n, qs, nq, cqs, nc, cvals, false, &tg);
       if (trc) return trc;
+      ctx->last_kernel = ctx->tune.tc > 0 && ctx->tune.tc < 3 ? (nq == 4 ? "k_gate_tc<4>" : "k_gate_tc<5>")
+                                                                : (nq == 4 ? "k_gate_tca<4>" : "k_gate_tca<5>");
       return launch_tc_f32(ctx, st, tg, nq, qs[0] == 0, m);
     }
   }
@@ -278,6 +283,7 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
       TileGeom t;
       int trc = make_tile_geom(n, qs, nq, cqs, nc, cvals, &t);
       if (trc == QB200_OK) {
+        ctx->last_kernel = "k_gate_tile<4>";
         return t.pair ? launch_tile<4, true, 256, 3, 2>(ctx, st, t, m)
                       : launch_tile<4, false, 256, 3, 2>(ctx, st, t, m);
       }
@@ -294,6 +300,8 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
       Geom tg;
       int trc = make_geom(n, qs, nq, cqs, nc, cvals, false, &tg);
       if (trc) return trc;
+      ctx->last_kernel = EXPECT ? (nq == 4 ? "k_gate_tcx<4,expect>" : nq == 5 ? "k_gate_tcx<5,expect>" : "k_gate_tcx<6,expect>")
+                                : "k_gate_tcx<6>";
       return launch_tcx_f32(ctx, st, tg, nq, qs[0] == 0, m, EXPECT, out);
     }
   }
@@ -307,6 +315,7 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
       Geom dg;
       int drc = make_geom(n, qs, nq, cqs, nc, cvals, false, &dg);
       if (drc) return drc;
+      ctx->last_kernel = "k_gate_dbig";
       if (nq == 4) { if constexpr (EXPECT) return launch_dbig<4, true>(ctx, st, dg, m, out); }
       if (nq == 5) return launch_dbig<5, EXPECT>(ctx, st, dg, m, out);
       if (nq == 6) return launch_dbig<6, EXPECT>(ctx, st, dg, m, out);
@@ -318,7 +327,10 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
     if (!ctx->tune.force_generic && (nq == 5 || nq == 6) && aligned16 && ctx->tune.big != 0) {
       TileGeom t;
       int trc = make_tile_geom(n, qs, nq, cqs, nc, cvals, &t);
-      if (trc == QB200_OK) return launch_big_f32(ctx, st, t, nq, m, EXPECT, out);
+      if (trc == QB200_OK) {
+        ctx->last_kernel = nq == 5 ? "k_gate_big<5>" : "k_gate_big<6>";
+        return launch_big_f32(ctx, st, t, nq, m, EXPECT, out);
+      }
       if (trc != QB200_ERR_UNSUPPORTED) return trc;
     }
   }
@@ -331,8 +343,18 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
     // expansion is NOT needed (bit 0 is already a special position); nothing to do.
   }
 
-  if (generic) return launch_generic<FP, EXPECT>(ctx, st, g, nq, m, out);
+  if (generic) {
+    ctx->last_kernel = "k_gate_generic";
+    return launch_generic<FP, EXPECT>(ctx, st, g, nq, m, out);
+  }
 
+  {
+    static const char* const kRegNames[2][6] = {
+        {"k_gate_reg<0>", "k_gate_reg<1>", "k_gate_reg<2>", "k_gate_reg<3>", "k_gate_reg<4>", "k_gate_reg<5>"},
+        {"k_expect<0>", "k_expect<1>", "k_expect<2>", "k_expect<3>", "k_expect<4>", "k_expect<5>"}};
+    if (nq <= 5) ctx->last_kernel = kRegNames[EXPECT ? 1 : 0][nq];
+    if (sizeof(FP) == 4 && !EXPECT && nq == 4 && ctx->tune.tile != 0) ctx->last_kernel = "k_gate_pipe<4>";
+  }
   switch (nq) {
     case 0: return launch_reg_mode<FP, 0, EXPECT>(ctx, mode, st, g, m, out);
     case 1: return launch_reg_mode<FP, 1, EXPECT>(ctx, mode, st, g, m, out);
@@ -345,6 +367,7 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
       break;
     default: break;
   }
+  ctx->last_kernel = "k_gate_generic";
   return launch_generic<FP, EXPECT>(ctx, st, g, nq, m, out);
 }
 

@@ -15,6 +15,7 @@ int expect_monomial_f32(qb200_ctx* ctx, const float* st, unsigned n, const unsig
                         double* out);
 int expect_monomial_f64(qb200_ctx* ctx, const double* st, unsigned n, const unsigned* qs, unsigned nq, const double* m,
                         double* out);
+int batch_zero_slot(qb200_ctx* ctx);
 }  // namespace qb200
 
 using namespace qb200;
@@ -48,7 +49,10 @@ int qb200_expectation_value(qb200_ctx* ctx, int dtype, const void* state, unsign
                             double out_re_im[2]) {
   if (!out_re_im) return QB200_ERR_INVALID;
   out_re_im[0] = out_re_im[1] = 0;  // the reference returns 0 for unsupported sizes (:259)
-  if (num_targets > kMaxTargets) return QB200_ERR_UNSUPPORTED;
+  if (num_targets > kMaxTargets) {
+    if (ctx) (void) batch_zero_slot(ctx);
+    return QB200_ERR_UNSUPPORTED;
+  }
   // Pauli strings and other XOR-monomial operators: a read pass without a mat-vec (expect_monomial.cu).  G <= 2
   // stays on k_expect_stream, which is at the read roofline already.
   if (ctx && num_targets >= 3 && ctx->tune.mono != 0 && (dtype == QB200_F32 || dtype == QB200_F64)) {

@@ -19,7 +19,8 @@ int launch_big_shape(qb200_ctx* ctx, float* st, const TileGeom& t, const float* 
   auto kern = k_gate_big<G, PAIR, EXPECT, NT, D>;
   constexpr int warps = NT / 32;
   constexpr size_t smem = (size_t) warps * D * (8 << (G + 5)) + (8 << (G + 5));
-  static const int occ = [&] {
+  static PerDevice occ_cache;
+  const int occ = occ_cache.get(ctx, [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem) != cudaSuccess || nb < 1) {
@@ -27,9 +28,9 @@ int launch_big_shape(qb200_ctx* ctx, float* st, const TileGeom& t, const float* 
       nb = 1;
     }
     return nb;
-  }();
+  });
   const uint64_t need = (t.work + warps - 1) / warps;
-  uint64_t persistent = uint64_t{kNumSMs} * occ;
+  uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
   if (EXPECT && persistent > kExpectMaxBlocks) persistent = kExpectMaxBlocks;
   const uint32_t blocks = (uint32_t) (need < persistent ? need : persistent);
 

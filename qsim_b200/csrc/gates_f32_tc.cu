@@ -13,7 +13,8 @@ template <int G, bool PAIR, int NBUF, int PF, int MINB>
 int launch_tc_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
   auto kern = k_gate_tc<G, PAIR, NBUF, PF, MINB>;
   constexpr size_t smem = tc_smem_bytes<G, NBUF>();
-  static const int occ = [&] {
+  static PerDevice occ_cache;
+  const int occ = occ_cache.get(ctx, [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // resident CTAs per SM: shared memory (227 KB usable, 1 KB reserved per CTA) and TMEM
@@ -26,11 +27,11 @@ int launch_tc_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
     if (nb < 1) nb = 1;
     if (getenv("QB200_VERBOSE")) fprintf(stderr, "k_gate_tc<%d>: smem %zu, blocks per SM %d\n", G, smem, nb);
     return nb;
-  }();
+  });
   MatParam<float, G> mat;
   mat.fill(m);
   const uint64_t tiles = g.work >> 7;
-  const uint64_t persistent = uint64_t{kNumSMs} * occ;
+  const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
   const uint32_t blocks = (uint32_t) (tiles < persistent ? tiles : persistent);
   kern<<<blocks, kTcThreads, smem, ctx->stream>>>(st, g, mat);
   QB_LAUNCHED(ctx);
@@ -42,7 +43,8 @@ template <int G, bool PAIR, int NBUF, int PF, int MT, bool COMP, int RING, int M
 int launch_tca_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
   auto kern = k_gate_tca<G, PAIR, NBUF, PF, MT, COMP, RING, MINB>;
   constexpr size_t smem = tca_smem_bytes<G, RING, MT>();
-  static const int occ = [&] {
+  static PerDevice occ_cache;
+  const int occ = occ_cache.get(ctx, [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     int nb = 512 / tca_tmem_cols<G, NBUF * MT>();  // tensor memory (and 2048 threads) bound the residency
     if (nb * kTcThreads * MT > 2048) nb = 2048 / (kTcThreads * MT);
@@ -52,11 +54,11 @@ int launch_tca_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
     if (nb < 1) nb = 1;
     if (getenv("QB200_VERBOSE")) fprintf(stderr, "k_gate_tca<%d>: smem %zu, blocks per SM %d\n", G, smem, nb);
     return nb;
-  }();
+  });
   MatParam<float, G> mat;
   mat.fill(m);
   const uint64_t tiles = g.work >> 7 >> (MT - 1);
-  const uint64_t persistent = uint64_t{kNumSMs} * occ;
+  const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
   const uint32_t blocks = (uint32_t) (tiles < persistent ? tiles : persistent);
   kern<<<blocks, kTcThreads * MT, smem, ctx->stream>>>(st, g, mat);
   QB_LAUNCHED(ctx);
@@ -72,7 +74,8 @@ int launch_tcx_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m, d
   constexpr size_t smem = tcx_smem_bytes<G>();
   // resident CTAs per SM: TMEM columns (the allocation is the next power of two of 3 * KF), shared
   // memory and registers (the runtime's occupancy query answers 1 for kernels that allocate TMEM)
-  static const int occ = [&] {
+  static PerDevice occ_cache;
+  const int occ = occ_cache.get(ctx, [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     int nb = 512 / tca_tmem_cols<G, 1>();
     const int smem_limit = (int) ((227 * 1024) / (smem + 1024 + 64));
@@ -85,9 +88,9 @@ int launch_tcx_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m, d
     if (nb < 1) nb = 1;
     if (getenv("QB200_VERBOSE")) fprintf(stderr, "k_gate_tcx<%d,%d>: smem %zu, blocks per SM %d\n", G, (int) EXPECT, smem, nb);
     return nb;
-  }();
+  });
   const uint64_t tiles = g.work >> 7;
-  uint64_t persistent = uint64_t{kNumSMs} * occ;
+  uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
   if (EXPECT && persistent > kExpectMaxBlocks) persistent = kExpectMaxBlocks;
   const uint32_t blocks = (uint32_t) (tiles < persistent ? tiles : persistent);
   double* partials = nullptr;

@@ -217,16 +217,17 @@ int one_qubit_moments(qb200_ctx* ctx, const FP* st, unsigned n, double* out) {
   if (reinterpret_cast<uintptr_t>(st) & 15) return QB200_ERR_UNSUPPORTED;  // 128-bit loads
   const unsigned T = std::min<unsigned>(TMAX, n), L = std::min<unsigned>(4, T);
   auto kern = k_moments<FP, TMAX, MINB>;
-  static const int occ = [&] {
+  static PerDevice occ_cache;
+  const int occ = occ_cache.get(ctx, [&] {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kMomNT, 0) != cudaSuccess || nb < 1) {
       (void) cudaGetLastError();
       nb = 1;
     }
     return nb;
-  }();
+  });
   const uint64_t ntiles = uint64_t{1} << (n - T);
-  const uint32_t blocks = (uint32_t) std::min<uint64_t>(ntiles, uint64_t{kNumSMs} * occ);
+  const uint32_t blocks = (uint32_t) std::min<uint64_t>(ntiles, uint64_t(grid_sms(ctx)) * occ);
   const size_t pdoubles = size_t{blocks} * kMomMaxT * 4;
   int rc = ensure_scratch(ctx, (pdoubles + 4 * size_t{n}) * sizeof(double));
   if (rc) return rc;

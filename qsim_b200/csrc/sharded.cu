@@ -1,0 +1,1273 @@
+// sharded.cu -- a state of n qubits sharded over 2^g GPUs by global qubits, behind the C ABI (qb200_sv_*).
+//
+// What the reference only reaches through the closed cuStateVecEx library -- the multi-device State of
+// lib/vectorspace_custatevecex.h:189-287,385-470, its wire ordering (:163-177), the index-bit swaps of
+// lib/simulator_custatevecex.h:147-196 and the scheduler behind custatevecExSVUpdaterApply
+// (lib/run_custatevecex.h:243-305) -- built here from the single-GPU kernels of this library plus
+//   * a qubit map (logical qubit -> physical index bit; the top g physical bits are the shard number),
+//   * ONE exchange kernel per GPU that pushes a shard's amplitudes straight into the peers' memory over NVLink
+//     while re-packing the local index bits (k_remap_push; in place through k_p2p_swap when a second buffer does
+//     not fit), bracketed by stream-ordered barriers (events inside one process, flag words in peer memory
+//     between processes) -- no host synchronisation, no NCCL, no PyTorch,
+//   * the look-ahead, reordering swap planner of sv_plan.h.
+// Two ways to own the shards: one process drives all devices (qb200_sv_create; a device may hold several shards,
+// which is how a single-GPU box tests this file), or one process per GPU (qb200_sv_create_mp; the caller supplies
+// allgather / allreduce / barrier callbacks, the analogue of custatevecExCommunicator,
+// lib/multiprocess_custatevecex.h:82-87).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "sv_plan.h"
+
+namespace qb200 {
+
+constexpr unsigned kMaxGlobal = 5;        // up to 32 shards
+constexpr unsigned kMaxShards = 1u << kMaxGlobal;
+constexpr unsigned kMinInplaceBit = 4;    // in-place exchange: victims below this bit are lifted first (short runs)
+
+// ---------------------------------------------------------------------------------------------------------
+// exchange kernel, out of place: every amplitude of the local shard goes to its place in the NEW layout, which
+// is a buffer of this or of a peer GPU.  The k victim bits of the local index select the destination shard; the
+// remaining local bits are packed (order kept) into the low n_local - k bits of the new local index and this
+// shard's own value of the k exchanged rank bits becomes the top k bits.  Reads are local and contiguous; a
+// warp's 16-byte stores fall into runs of 2^lbits[0] amplitudes per destination, and because the packed index
+// keeps those runs adjacent, a warp writes whole 128-byte lines whatever the victim bits are -- no local SWAP
+// passes in front of the exchange.  Push only: nothing is read over NVLink.
+// ---------------------------------------------------------------------------------------------------------
+struct RemapGeom {
+  void* dst[kMaxShards];   // new buffer of the shard whose exchanged rank bits equal v
+  uint64_t items;          // vector items in the shard
+  uint32_t k, my, vshift, nl;
+  uint32_t lbits[kMaxGlobal];  // ascending
+};
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+k_remap_push(const V* __restrict__ src, const __grid_constant__ RemapGeom g) {
+  constexpr int U = 4;
+  const uint64_t stride = uint64_t{gridDim.x} * blockDim.x;
+  for (uint64_t t0 = blockIdx.x * uint64_t{blockDim.x} + threadIdx.x; t0 < g.items; t0 += stride * U) {
+    V x[U];
+    uint64_t t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      t[u] = t0 + u * stride;
+      if (t[u] < g.items) x[u] = src[t[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (t[u] >= g.items) continue;
+      uint64_t idx = t[u] << g.vshift;   // amplitude index of the item's first amplitude
+      uint32_t v = 0;
+      // remove the victim bits, highest first, collecting their values
+      for (int j = (int) g.k - 1; j >= 0; --j) {
+        const uint32_t b = g.lbits[j];
+        v |= (uint32_t) ((idx >> b) & 1) << j;
+        const uint64_t lo = idx & ((uint64_t{1} << b) - 1);
+        idx = ((idx >> (b + 1)) << b) | lo;
+      }
+      idx |= uint64_t{g.my} << (g.nl - g.k);
+      reinterpret_cast<V*>(g.dst[v])[idx >> g.vshift] = x[u];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// flag barrier between shards that live in different processes: shard `me` writes the epoch into its slot of
+// every peer's flag array (release, system scope) and waits until all its own slots carry it.  One warp.
+// A peer that never arrives trips the timeout instead of hanging the GPU; the error word is mapped host memory.
+// ---------------------------------------------------------------------------------------------------------
+struct FlagGeom {
+  uint32_t* flags[kMaxShards];  // flag array of shard r (P words), addressable from this device
+  uint32_t P, me, epoch;
+  uint32_t* err;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(32) k_flag_barrier(const __grid_constant__ FlagGeom g) {
+  __threadfence_system();
+  for (uint32_t s = threadIdx.x; s < g.P; s += 32) {
+    if (s == g.me) continue;
+    st_release_sys(g.flags[s] + g.me, g.epoch);
+  }
+  const uint64_t t0 = global_ns();
+  for (uint32_t s = threadIdx.x; s < g.P; s += 32) {
+    if (s == g.me) continue;
+    while ((int32_t) (ld_acquire_sys(g.flags[g.me] + s) - g.epoch) < 0) {
+      __nanosleep(200);
+      if (global_ns() - t0 > 20000000000ull) {  // 20 s: a peer died
+        *g.err = 1;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+struct Shard {
+  int device = 0;
+  unsigned rank = 0;
+  qb200_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  void* buf[2] = {nullptr, nullptr};
+  uint32_t* flags = nullptr;
+  cudaEvent_t ev = nullptr;
+};
+
+struct SvStats {
+  uint64_t swaps = 0, local_passes = 0, gate_passes = 0;
+  double bytes_sent_per_shard = 0;   // summed over swaps
+  double exchange_ms = 0;            // device time (events on the first local shard's stream)
+};
+
+}  // namespace qb200
+
+using namespace qb200;
+
+struct qb200_sv {
+  unsigned n = 0, g = 0, nl = 0, P = 1;
+  int dtype = QB200_F32;
+  bool mp = false;
+  unsigned rank = 0;                     // mp: this process's shard
+  qb200_comm comm{};
+  std::vector<Shard> sh;                 // local shards
+  int cur = 0;                           // buf[cur] holds the state on every shard
+  bool have_alt = false, alt_failed = false;
+  std::vector<void*> peer_buf[2];        // [b][rank] addressable from the local devices (own entries = local pointers)
+  std::vector<uint32_t*> peer_flags;
+  std::vector<void*> ipc_opened;         // mappings to close
+  std::vector<unsigned> pos;             // logical qubit -> physical bit
+  std::vector<uint64_t> last_use;        // LRU clock for the online path
+  uint64_t clock = 0;
+  uint32_t epoch = 0;
+  uint32_t* err_host = nullptr;          // mapped pinned
+  uint32_t* err_dev = nullptr;
+  int barrier_flags = 0;                 // 1: flag kernels (always in mp mode); 0: events
+  int swap_mode = -1;                    // -1 auto (out of place when the second buffer fits), 0 in place, 1 out of place
+  int reorder = 1;
+  SvStats stats;
+  std::vector<uint64_t> plan_key;        // gate structure + global set the cached schedule was made for
+  std::vector<int64_t> plan_steps;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;  // exchange timing, first local shard
+  size_t ev_used = 0;
+  int last_error = 0;
+};
+
+namespace qb200 {
+
+static size_t scalar_size(int dtype) { return dtype == QB200_F32 ? 4 : 8; }
+static size_t shard_bytes(const qb200_sv* sv) { return (size_t{2} << sv->nl) * scalar_size(sv->dtype); }
+
+#define SV_CUDA(sv, call)                                 \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) {                             \
+      (sv)->last_error = (int) e__;                       \
+      (void) cudaGetLastError();                          \
+      return e__ == cudaErrorMemoryAllocation ? QB200_ERR_OOM : QB200_ERR_CUDA; \
+    }                                                     \
+  } while (0)
+
+#define SV_TRY(expr)           \
+  do {                         \
+    int rc__ = (expr);         \
+    if (rc__ != QB200_OK) return rc__; \
+  } while (0)
+
+struct DevScope {
+  explicit DevScope(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); }
+  ~DevScope() { int now; cudaGetDevice(&now); if (now != prev) cudaSetDevice(prev); }
+  int prev = 0;
+};
+
+static inline void* cur_buf(const qb200_sv* sv, const Shard& s) { return s.buf[sv->cur]; }
+
+static unsigned qubit_at(const qb200_sv* sv, unsigned phys) {
+  for (unsigned q = 0; q < sv->n; ++q)
+    if (sv->pos[q] == phys) return q;
+  return sv->n;
+}
+
+static bool canonical(const qb200_sv* sv) {
+  for (unsigned q = 0; q < sv->n; ++q)
+    if (sv->pos[q] != q) return false;
+  return true;
+}
+
+// logical amplitude index -> physical index
+static uint64_t to_physical(const qb200_sv* sv, uint64_t i) {
+  uint64_t p = 0;
+  for (unsigned q = 0; q < sv->n; ++q) p |= ((i >> q) & 1) << sv->pos[q];
+  return p;
+}
+static uint64_t to_logical(const qb200_sv* sv, uint64_t p) {
+  uint64_t i = 0;
+  for (unsigned q = 0; q < sv->n; ++q) i |= ((p >> sv->pos[q]) & 1) << q;
+  return i;
+}
+
+static Shard* local_shard(qb200_sv* sv, unsigned rank) {
+  for (auto& s : sv->sh)
+    if (s.rank == rank) return &s;
+  return nullptr;
+}
+
+static int sum_over_ranks(qb200_sv* sv, double* v, uint64_t count) {
+  if (!sv->mp) return QB200_OK;
+  return sv->comm.allreduce_sum_f64(sv->comm.user, v, count) == 0 ? QB200_OK : QB200_ERR_INVALID;
+}
+
+// ---- barriers -----------------------------------------------------------------------------------------
+static int barrier(qb200_sv* sv) {
+  if (sv->P == 1) return QB200_OK;
+  if (!sv->barrier_flags) {
+    for (auto& s : sv->sh) {
+      DevScope d(s.device);
+      SV_CUDA(sv, cudaEventRecord(s.ev, s.stream));
+    }
+    for (auto& s : sv->sh) {
+      DevScope d(s.device);
+      for (auto& t : sv->sh)
+        if (&t != &s) SV_CUDA(sv, cudaStreamWaitEvent(s.stream, t.ev, 0));
+    }
+    return QB200_OK;
+  }
+  ++sv->epoch;
+  for (auto& s : sv->sh) {
+    DevScope d(s.device);
+    FlagGeom fg{};
+    for (unsigned r = 0; r < sv->P; ++r) fg.flags[r] = sv->peer_flags[r];
+    fg.P = sv->P;
+    fg.me = s.rank;
+    fg.epoch = sv->epoch;
+    fg.err = sv->err_dev;
+    k_flag_barrier<<<1, 32, 0, s.stream>>>(fg);
+    ++s.ctx->launches;
+    SV_CUDA(sv, cudaPeekAtLastError());
+  }
+  return QB200_OK;
+}
+
+static int sync_all(qb200_sv* sv) {
+  for (auto& s : sv->sh) {
+    DevScope d(s.device);
+    SV_CUDA(sv, cudaStreamSynchronize(s.stream));
+  }
+  if (sv->err_host && *sv->err_host) return QB200_ERR_CUDA;  // a flag barrier timed out
+  return QB200_OK;
+}
+
+// ---- creation -------------------------------------------------------------------------------------------
+static int make_shard(qb200_sv* sv, int device, unsigned rank) {
+  Shard s;
+  s.device = device;
+  s.rank = rank;
+  SV_TRY(qb200_ctx_create(device, &s.ctx));
+  DevScope d(device);
+  SV_CUDA(sv, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  qb200_ctx_set_stream(s.ctx, s.stream);
+  SV_CUDA(sv, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  int rc = qb200_state_alloc_on(s.ctx, sv->nl, sv->dtype, &s.buf[0]);
+  if (rc) { sv->sh.push_back(s); return rc; }
+  SV_CUDA(sv, cudaMalloc((void**) &s.flags, 256 * sizeof(uint32_t)));
+  SV_CUDA(sv, cudaMemset(s.flags, 0, 256 * sizeof(uint32_t)));
+  sv->sh.push_back(s);
+  return QB200_OK;
+}
+
+static int init_common(qb200_sv* sv, unsigned num_shards, unsigned num_qubits, int dtype) {
+  unsigned g = 0;
+  while ((1u << g) < num_shards) ++g;
+  if ((1u << g) != num_shards || g > kMaxGlobal) return QB200_ERR_INVALID;
+  if (dtype != QB200_F32 && dtype != QB200_F64) return QB200_ERR_INVALID;
+  // same guard as lib/multiprocess_custatevecex.h:160-163: at least two local qubits
+  if (num_qubits < g + 2 || num_qubits > kMaxQubits) return QB200_ERR_INVALID;
+  sv->n = num_qubits;
+  sv->g = g;
+  sv->nl = num_qubits - g;
+  sv->P = num_shards;
+  sv->dtype = dtype;
+  sv->pos.resize(num_qubits);
+  for (unsigned q = 0; q < num_qubits; ++q) sv->pos[q] = q;
+  sv->last_use.assign(num_qubits, 0);
+  sv->peer_buf[0].assign(num_shards, nullptr);
+  sv->peer_buf[1].assign(num_shards, nullptr);
+  sv->peer_flags.assign(num_shards, nullptr);
+  if (cudaHostAlloc((void**) &sv->err_host, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return QB200_ERR_CUDA;
+  }
+  *sv->err_host = 0;
+  if (cudaHostGetDevicePointer((void**) &sv->err_dev, sv->err_host, 0) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return QB200_ERR_CUDA;
+  }
+  return QB200_OK;
+}
+
+static int allgather_ipc(qb200_sv* sv, void* mine, std::vector<void*>* table) {
+  std::vector<unsigned char> send(64), recv(size_t{64} * sv->P);
+  SV_TRY(qb200_ipc_export(mine, send.data()));
+  if (sv->comm.allgather(sv->comm.user, send.data(), recv.data(), 64) != 0) return QB200_ERR_INVALID;
+  for (unsigned r = 0; r < sv->P; ++r) {
+    if (r == sv->rank) { (*table)[r] = mine; continue; }
+    void* p = nullptr;
+    SV_TRY(qb200_ipc_import(recv.data() + size_t{64} * r, &p));
+    sv->ipc_opened.push_back(p);
+    (*table)[r] = p;
+  }
+  return QB200_OK;
+}
+
+// second buffer per shard for the out-of-place exchange; collective decision in mp mode
+static int ensure_alt(qb200_sv* sv) {
+  if (sv->have_alt) return QB200_OK;
+  if (sv->alt_failed || sv->cur != 0) return QB200_ERR_OOM;  // cur only leaves slot 0 once the spare exists
+  bool ok = true;
+  for (auto& s : sv->sh) {
+    if (s.buf[1]) continue;
+    if (qb200_state_alloc_on(s.ctx, sv->nl, sv->dtype, &s.buf[1]) != QB200_OK) { ok = false; break; }
+  }
+  if (sv->mp) {
+    double v = ok ? 0.0 : 1.0;
+    SV_TRY(sum_over_ranks(sv, &v, 1));
+    ok = v == 0.0;
+  }
+  if (!ok) {
+    for (auto& s : sv->sh)
+      if (s.buf[1]) { DevScope d(s.device); cudaFree(s.buf[1]); s.buf[1] = nullptr; }
+    sv->alt_failed = true;
+    return QB200_ERR_OOM;
+  }
+  if (sv->mp) {
+    std::vector<void*> table(sv->P, nullptr);
+    SV_TRY(allgather_ipc(sv, sv->sh[0].buf[1], &table));
+    for (unsigned r = 0; r < sv->P; ++r) sv->peer_buf[1][r] = table[r];
+  } else {
+    for (auto& s : sv->sh) sv->peer_buf[1][s.rank] = s.buf[1];
+  }
+  sv->have_alt = true;
+  return QB200_OK;
+}
+
+// ---- local gate on every shard ----------------------------------------------------------------------------
+template <typename FP>
+static void permute_matrix(const FP* m, unsigned nq, const unsigned* order, std::vector<FP>* out) {
+  // new index bit j <-> old index bit order[j]
+  const unsigned dim = 1u << nq;
+  std::vector<unsigned> map(dim);
+  for (unsigned a = 0; a < dim; ++a) {
+    unsigned o = 0;
+    for (unsigned j = 0; j < nq; ++j) o |= ((a >> j) & 1u) << order[j];
+    map[a] = o;
+  }
+  out->resize(size_t{2} * dim * dim);
+  for (unsigned r = 0; r < dim; ++r)
+    for (unsigned c = 0; c < dim; ++c) {
+      (*out)[2 * (size_t{r} * dim + c)] = m[2 * (size_t{map[r]} * dim + map[c])];
+      (*out)[2 * (size_t{r} * dim + c) + 1] = m[2 * (size_t{map[r]} * dim + map[c]) + 1];
+    }
+}
+
+// Applies a gate (expect = false) or evaluates an operator (expect = true, result summed over the local shards
+// into out[2]) whose TARGETS are all local.  Controls may be global: they select the shards that take part.
+static int local_gate(qb200_sv* sv, const unsigned* qs, unsigned nq, const unsigned* cqs, unsigned nc,
+                      uint64_t cvals, const void* matrix, bool expect, double* out) {
+  if (nq > kMaxTargets) return QB200_ERR_UNSUPPORTED;
+  if (nc > 0 && nq > kMaxCtrlTargets) return QB200_ERR_UNSUPPORTED;
+  unsigned phys[kMaxTargets], order[kMaxTargets], sorted[kMaxTargets];
+  for (unsigned j = 0; j < nq; ++j) {
+    if (qs[j] >= sv->n) return QB200_ERR_INVALID;
+    phys[j] = sv->pos[qs[j]];
+    if (phys[j] >= sv->nl) return QB200_ERR_INVALID;  // caller must have made it local
+    order[j] = j;
+  }
+  std::sort(order, order + nq, [&](unsigned a, unsigned b) { return phys[a] < phys[b]; });
+  bool identity = true;
+  for (unsigned j = 0; j < nq; ++j) {
+    sorted[j] = phys[order[j]];
+    identity &= order[j] == j;
+  }
+  std::vector<float> mf;
+  std::vector<double> md;
+  const void* m = matrix;
+  if (!identity) {
+    if (sv->dtype == QB200_F32) { permute_matrix((const float*) matrix, nq, order, &mf); m = mf.data(); }
+    else { permute_matrix((const double*) matrix, nq, order, &md); m = md.data(); }
+  }
+  // controls: bit i of cvals <-> i-th lowest control qubit (lib/simulator.h:364-375)
+  std::vector<std::pair<unsigned, unsigned>> ctl;  // (logical, value)
+  {
+    std::vector<unsigned> c(cqs, cqs + nc);
+    std::vector<unsigned> idx(nc);
+    for (unsigned i = 0; i < nc; ++i) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](unsigned a, unsigned b) { return c[a] < c[b]; });
+    for (unsigned i = 0; i < nc; ++i) {
+      if (c[idx[i]] >= sv->n) return QB200_ERR_INVALID;
+      ctl.emplace_back(c[idx[i]], (unsigned) ((cvals >> i) & 1));
+    }
+  }
+  std::vector<std::pair<unsigned, unsigned>> lctl;  // (physical local bit, value)
+  uint64_t gmask = 0, gbits = 0;
+  for (auto& cv : ctl) {
+    const unsigned p = sv->pos[cv.first];
+    if (p >= sv->nl) {
+      gmask |= uint64_t{1} << (p - sv->nl);
+      gbits |= uint64_t{cv.second} << (p - sv->nl);
+    } else {
+      lctl.emplace_back(p, cv.second);
+    }
+  }
+  std::sort(lctl.begin(), lctl.end());
+  unsigned lc[64];
+  uint64_t lcv = 0;
+  for (size_t i = 0; i < lctl.size(); ++i) {
+    lc[i] = lctl[i].first;
+    lcv |= uint64_t{lctl[i].second} << i;
+  }
+  if (expect) {
+    for (auto& s : sv->sh) SV_TRY(qb200_reduce_batch_begin(s.ctx, 1));
+  }
+  int rc = QB200_OK;
+  for (auto& s : sv->sh) {
+    if ((s.rank & gmask) != gbits) continue;
+    if (expect) {
+      double dummy[2];
+      rc = qb200_expectation_value(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, sorted, nq, m, dummy);
+    } else {
+      rc = qb200_apply_controlled_gate(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, sorted, nq, lc,
+                                       (unsigned) lctl.size(), lcv, m);
+    }
+    if (rc) break;
+  }
+  if (expect) {
+    out[0] = out[1] = 0;
+    for (auto& s : sv->sh) {
+      double r[4] = {0, 0, 0, 0};
+      uint32_t cnt = 0;
+      int rc2 = qb200_reduce_batch_end(s.ctx, r, 2, &cnt);
+      if (rc2 && !rc) rc = rc2;
+      if (cnt) { out[0] += r[0]; out[1] += r[1]; }
+    }
+  } else {
+    ++sv->stats.gate_passes;
+  }
+  return rc;
+}
+
+static const float kSwapF[32] = {1, 0, 0, 0, 0, 0, 0, 0,  0, 0, 0, 0, 1, 0, 0, 0,
+                                 0, 0, 1, 0, 0, 0, 0, 0,  0, 0, 0, 0, 0, 0, 1, 0};
+static const double kSwapD[32] = {1, 0, 0, 0, 0, 0, 0, 0,  0, 0, 0, 0, 1, 0, 0, 0,
+                                  0, 0, 1, 0, 0, 0, 0, 0,  0, 0, 0, 0, 0, 0, 1, 0};
+
+// exchanges two LOCAL physical bits with one 2-qubit SWAP pass (exact: products with 0 and 1 on the FFMA kernels)
+static int local_bit_swap(qb200_sv* sv, unsigned pa, unsigned pb) {
+  if (pa == pb) return QB200_OK;
+  const unsigned qa = qubit_at(sv, pa), qb = qubit_at(sv, pb);
+  unsigned bits[2] = {std::min(pa, pb), std::max(pa, pb)};
+  for (auto& s : sv->sh)
+    SV_TRY(qb200_apply_gate(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, bits, 2,
+                            sv->dtype == QB200_F32 ? (const void*) kSwapF : (const void*) kSwapD));
+  sv->pos[qa] = pb;
+  sv->pos[qb] = pa;
+  ++sv->stats.local_passes;
+  return QB200_OK;
+}
+
+// ---- the exchange ---------------------------------------------------------------------------------------------
+static unsigned with_bits(unsigned rank, const unsigned* gb, unsigned k, unsigned v) {
+  for (unsigned j = 0; j < k; ++j) rank = (rank & ~(1u << gb[j])) | (((v >> j) & 1u) << gb[j]);
+  return rank;
+}
+static unsigned pick_bits(unsigned rank, const unsigned* gb, unsigned k) {
+  unsigned v = 0;
+  for (unsigned j = 0; j < k; ++j) v |= ((rank >> gb[j]) & 1u) << j;
+  return v;
+}
+
+static void timing_begin(qb200_sv* sv) {
+  if (sv->ev_used == sv->ev_pairs.size()) {
+    DevScope d(sv->sh[0].device);
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    sv->ev_pairs.emplace_back(a, b);
+  }
+  DevScope d(sv->sh[0].device);
+  cudaEventRecord(sv->ev_pairs[sv->ev_used].first, sv->sh[0].stream);
+}
+static void timing_end(qb200_sv* sv) {
+  DevScope d(sv->sh[0].device);
+  cudaEventRecord(sv->ev_pairs[sv->ev_used].second, sv->sh[0].stream);
+  ++sv->ev_used;
+}
+static int timing_collect(qb200_sv* sv) {
+  SV_TRY(sync_all(sv));
+  for (size_t i = 0; i < sv->ev_used; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, sv->ev_pairs[i].first, sv->ev_pairs[i].second) == cudaSuccess) sv->stats.exchange_ms += ms;
+    else (void) cudaGetLastError();
+  }
+  sv->ev_used = 0;
+  return QB200_OK;
+}
+
+// victims (logical, local) <-> incoming (logical, global); k <= g.
+static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* incoming, unsigned k) {
+  if (k == 0) return QB200_OK;
+  if (k > sv->g) return QB200_ERR_INVALID;
+  std::vector<unsigned> victims(victims_in, victims_in + k);
+  unsigned gb[kMaxGlobal];
+  for (unsigned j = 0; j < k; ++j) {
+    if (victims[j] >= sv->n || incoming[j] >= sv->n) return QB200_ERR_INVALID;
+    if (sv->pos[victims[j]] >= sv->nl || sv->pos[incoming[j]] < sv->nl) return QB200_ERR_INVALID;
+    gb[j] = sv->pos[incoming[j]] - sv->nl;
+  }
+  bool out_of_place = sv->swap_mode != 0;
+  if (out_of_place && ensure_alt(sv) != QB200_OK) {
+    if (sv->swap_mode == 1) return QB200_ERR_OOM;
+    out_of_place = false;
+  }
+  const double sent = (double) shard_bytes(sv) * (1.0 - 1.0 / (double) (1u << k));
+
+  if (out_of_place) {
+    // victims sorted by physical bit; victim j pairs with rank bit gb[j]
+    std::sort(victims.begin(), victims.end(), [&](unsigned a, unsigned b) { return sv->pos[a] < sv->pos[b]; });
+    RemapGeom rg{};
+    rg.k = k;
+    rg.nl = sv->nl;
+    for (unsigned j = 0; j < k; ++j) rg.lbits[j] = sv->pos[victims[j]];
+    const bool vec2 = sv->dtype == QB200_F32 && rg.lbits[0] >= 1;
+    rg.vshift = vec2 ? 1 : 0;
+    rg.items = (uint64_t{1} << sv->nl) >> rg.vshift;
+    const int nb = 1 - sv->cur;
+    timing_begin(sv);
+    for (auto& s : sv->sh) {
+      DevScope d(s.device);
+      rg.my = pick_bits(s.rank, gb, k);
+      for (unsigned v = 0; v < (1u << k); ++v) rg.dst[v] = sv->peer_buf[nb][with_bits(s.rank, gb, k, v)];
+      uint64_t blocks = (rg.items + 256 * 4 - 1) / (256 * 4);
+      const uint64_t cap = uint64_t{kNumSMs} * 8;
+      if (blocks > cap) blocks = cap;
+      if (blocks < 1) blocks = 1;
+      if (sv->dtype == QB200_F32 && vec2)
+        k_remap_push<float4><<<(uint32_t) blocks, 256, 0, s.stream>>>((const float4*) s.buf[sv->cur], rg);
+      else if (sv->dtype == QB200_F32)
+        k_remap_push<float2><<<(uint32_t) blocks, 256, 0, s.stream>>>((const float2*) s.buf[sv->cur], rg);
+      else
+        k_remap_push<double2><<<(uint32_t) blocks, 256, 0, s.stream>>>((const double2*) s.buf[sv->cur], rg);
+      ++s.ctx->launches;
+      SV_CUDA(sv, cudaPeekAtLastError());
+    }
+    SV_TRY(barrier(sv));
+    timing_end(sv);
+    sv->cur = nb;
+    // new map: the remaining local qubits keep their order in the low bits, incoming j sits at nl - k + j
+    std::vector<unsigned> vb(rg.lbits, rg.lbits + k);
+    for (unsigned q = 0; q < sv->n; ++q) {
+      const unsigned p = sv->pos[q];
+      if (p >= sv->nl) continue;
+      if (std::find(victims.begin(), victims.end(), q) != victims.end()) continue;
+      unsigned below = 0;
+      for (unsigned b : vb) below += b < p;
+      sv->pos[q] = p - below;
+    }
+    for (unsigned j = 0; j < k; ++j) {
+      sv->pos[victims[j]] = sv->nl + gb[j];
+      sv->pos[incoming[j]] = sv->nl - k + j;
+    }
+  } else {
+    // in place (k_p2p_swap): local bit <-> rank bit; low victims are lifted first, at most 3 bits per pass
+    for (unsigned off = 0; off < k; off += 3) {
+      const unsigned kk = std::min(3u, k - off);
+      std::vector<unsigned> taken;
+      for (unsigned j = 0; j < kk; ++j) taken.push_back(sv->pos[victims[off + j]]);
+      for (unsigned j = 0; j < kk; ++j) {
+        const unsigned p = sv->pos[victims[off + j]];
+        if (p >= kMinInplaceBit || sv->nl <= kMinInplaceBit + kk) continue;
+        unsigned dst = sv->nl;
+        for (unsigned c = sv->nl; c-- > kMinInplaceBit;)
+          if (std::find(taken.begin(), taken.end(), c) == taken.end()) { dst = c; break; }
+        if (dst == sv->nl) continue;
+        SV_TRY(local_bit_swap(sv, p, dst));
+        *std::find(taken.begin(), taken.end(), p) = dst;
+      }
+      // pair the victims (ascending physical bit) with the rank bits
+      std::vector<unsigned> ord(kk);
+      for (unsigned j = 0; j < kk; ++j) ord[j] = off + j;
+      std::sort(ord.begin(), ord.end(), [&](unsigned a, unsigned b) { return sv->pos[victims[a]] < sv->pos[victims[b]]; });
+      unsigned lb[3], g3[3];
+      for (unsigned j = 0; j < kk; ++j) { lb[j] = sv->pos[victims[ord[j]]]; g3[j] = gb[off + j]; }
+      timing_begin(sv);
+      SV_TRY(barrier(sv));
+      for (auto& s : sv->sh) {
+        void* peers[8] = {};
+        const unsigned my = pick_bits(s.rank, g3, kk);
+        for (unsigned v = 0; v < (1u << kk); ++v)
+          if (v != my) peers[v] = sv->peer_buf[sv->cur][with_bits(s.rank, g3, kk, v)];
+        SV_TRY(qb200_swap_global_local(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, peers, kk, lb, my));
+      }
+      SV_TRY(barrier(sv));
+      timing_end(sv);
+      for (unsigned j = 0; j < kk; ++j) {
+        sv->pos[victims[ord[j]]] = sv->nl + g3[j];
+        sv->pos[incoming[off + j]] = lb[j];
+      }
+    }
+  }
+  ++sv->stats.swaps;
+  sv->stats.bytes_sent_per_shard += sent;
+  return QB200_OK;
+}
+
+// brings every qubit of `qs` into the local part with one exchange; victims: LRU (online) local qubits outside qs
+static int make_local(qb200_sv* sv, const unsigned* qs, unsigned nq) {
+  std::vector<unsigned> incoming;
+  for (unsigned j = 0; j < nq; ++j) {
+    if (qs[j] >= sv->n) return QB200_ERR_INVALID;
+    if (sv->pos[qs[j]] >= sv->nl) incoming.push_back(qs[j]);
+  }
+  if (incoming.empty()) return QB200_OK;
+  if (nq > sv->nl) return QB200_ERR_INVALID;
+  std::vector<unsigned> cand;
+  for (unsigned q = 0; q < sv->n; ++q)
+    if (sv->pos[q] < sv->nl && std::find(qs, qs + nq, q) == qs + nq) cand.push_back(q);
+  std::stable_sort(cand.begin(), cand.end(), [&](unsigned a, unsigned b) {
+    if (sv->last_use[a] != sv->last_use[b]) return sv->last_use[a] < sv->last_use[b];
+    return sv->pos[a] > sv->pos[b];
+  });
+  if (cand.size() < incoming.size()) return QB200_ERR_INVALID;
+  cand.resize(incoming.size());
+  return exchange(sv, cand.data(), incoming.data(), (unsigned) incoming.size());
+}
+
+// restores pos[q] = q: at most two exchanges for the rank bits, then 2-qubit SWAP passes for the local bits
+static int canonicalize(qb200_sv* sv) {
+  if (canonical(sv)) return QB200_OK;
+  for (int iter = 0; iter < 4; ++iter) {
+    std::vector<unsigned> victims, incoming, stuck;
+    for (unsigned t = 0; t < sv->g; ++t) {
+      const unsigned want = sv->nl + t, have = qubit_at(sv, sv->nl + t);
+      if (have == want) continue;
+      if (sv->pos[want] < sv->nl) { victims.push_back(want); incoming.push_back(have); }
+      else stuck.push_back(have);
+    }
+    if (victims.empty() && stuck.empty()) break;
+    if (!victims.empty()) {
+      SV_TRY(exchange(sv, victims.data(), incoming.data(), (unsigned) victims.size()));
+      continue;
+    }
+    // the wanted qubits sit on other rank bits: bring all of them local first
+    std::vector<unsigned> spare;
+    for (unsigned p = sv->nl; p-- > 0 && spare.size() < stuck.size();) {
+      const unsigned q = qubit_at(sv, p);
+      if (q < sv->nl) spare.push_back(q);
+    }
+    if (spare.size() < stuck.size()) return QB200_ERR_INVALID;
+    SV_TRY(exchange(sv, spare.data(), stuck.data(), (unsigned) stuck.size()));
+  }
+  for (unsigned b = 0; b < sv->nl; ++b)
+    if (sv->pos[b] != b) SV_TRY(local_bit_swap(sv, b, sv->pos[b]));
+  return canonical(sv) ? QB200_OK : QB200_ERR_INVALID;
+}
+
+static void touch(qb200_sv* sv, const unsigned* qs, unsigned nq) {
+  ++sv->clock;
+  for (unsigned j = 0; j < nq; ++j) sv->last_use[qs[j]] = sv->clock;
+}
+
+}  // namespace qb200
+
+// =================================================================================================================
+extern "C" {
+
+int qb200_sv_create(const int* devices, unsigned num_shards, unsigned num_qubits, int dtype, qb200_sv** out) {
+  if (!out || !devices) return QB200_ERR_INVALID;
+  *out = nullptr;
+  qb200_sv* sv = new (std::nothrow) qb200_sv();
+  if (!sv) return QB200_ERR_OOM;
+  int rc = init_common(sv, num_shards, num_qubits, dtype);
+  for (unsigned r = 0; r < num_shards && rc == QB200_OK; ++r) rc = make_shard(sv, devices[r], r);
+  if (rc == QB200_OK) {
+    // peer access between distinct devices (shards on one device need none)
+    for (auto& a : sv->sh)
+      for (auto& b : sv->sh) {
+        if (a.device == b.device) continue;
+        DevScope d(a.device);
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, a.device, b.device);
+        if (!can) { rc = QB200_ERR_UNSUPPORTED; break; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { rc = QB200_ERR_CUDA; break; }
+        (void) cudaGetLastError();
+      }
+  }
+  if (rc != QB200_OK) {
+    qb200_sv_destroy(sv);
+    return rc;
+  }
+  for (auto& s : sv->sh) {
+    sv->peer_buf[0][s.rank] = s.buf[0];
+    sv->peer_flags[s.rank] = s.flags;
+  }
+  *out = sv;
+  return QB200_OK;
+}
+
+int qb200_sv_create_mp(int device, unsigned rank, unsigned world, const qb200_comm* comm, unsigned num_qubits,
+                       int dtype, qb200_sv** out) {
+  if (!out || !comm || !comm->allgather || !comm->allreduce_sum_f64 || !comm->barrier || rank >= world)
+    return QB200_ERR_INVALID;
+  *out = nullptr;
+  qb200_sv* sv = new (std::nothrow) qb200_sv();
+  if (!sv) return QB200_ERR_OOM;
+  sv->mp = true;
+  sv->rank = rank;
+  sv->comm = *comm;
+  sv->barrier_flags = 1;
+  int rc = init_common(sv, world, num_qubits, dtype);
+  if (rc == QB200_OK) rc = make_shard(sv, device, rank);
+  // every rank takes the same path from here on, whatever happened locally
+  double bad = rc == QB200_OK ? 0.0 : 1.0;
+  if (comm->allreduce_sum_f64(comm->user, &bad, 1) != 0 || bad != 0.0) {
+    qb200_sv_destroy(sv);
+    return rc != QB200_OK ? rc : QB200_ERR_OOM;
+  }
+  if (world > 1) {
+    rc = allgather_ipc(sv, sv->sh[0].buf[0], &sv->peer_buf[0]);
+    if (rc == QB200_OK) {
+      std::vector<void*> fl(world, nullptr);
+      rc = allgather_ipc(sv, sv->sh[0].flags, &fl);
+      for (unsigned r = 0; r < world; ++r) sv->peer_flags[r] = (uint32_t*) fl[r];
+    }
+    comm->barrier(comm->user);
+  } else {
+    sv->peer_buf[0][0] = sv->sh[0].buf[0];
+    sv->peer_flags[0] = sv->sh[0].flags;
+  }
+  if (rc != QB200_OK) {
+    qb200_sv_destroy(sv);
+    return rc;
+  }
+  *out = sv;
+  return QB200_OK;
+}
+
+int qb200_sv_destroy(qb200_sv* sv) {
+  if (!sv) return QB200_OK;
+  for (auto& s : sv->sh) {
+    DevScope d(s.device);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+  }
+  if (sv->mp && sv->P > 1 && sv->comm.barrier) sv->comm.barrier(sv->comm.user);  // nobody unmaps what a peer still uses
+  for (void* p : sv->ipc_opened) qb200_ipc_close(p);
+  for (auto& s : sv->sh) {
+    DevScope d(s.device);
+    if (s.buf[0]) cudaFree(s.buf[0]);
+    if (s.buf[1]) cudaFree(s.buf[1]);
+    if (s.flags) cudaFree(s.flags);
+    if (s.ev) cudaEventDestroy(s.ev);
+    if (s.ctx) qb200_ctx_destroy(s.ctx);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  for (auto& p : sv->ev_pairs) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  if (sv->err_host) cudaFreeHost(sv->err_host);
+  (void) cudaGetLastError();
+  delete sv;
+  return QB200_OK;
+}
+
+unsigned qb200_sv_num_qubits(const qb200_sv* sv) { return sv ? sv->n : 0; }
+unsigned qb200_sv_num_shards(const qb200_sv* sv) { return sv ? sv->P : 0; }
+unsigned qb200_sv_num_local_qubits(const qb200_sv* sv) { return sv ? sv->nl : 0; }
+int qb200_sv_last_cuda_error(const qb200_sv* sv) { return sv ? sv->last_error : 0; }
+
+int qb200_sv_qubit_map(const qb200_sv* sv, unsigned* pos) {
+  if (!sv || !pos) return QB200_ERR_INVALID;
+  for (unsigned q = 0; q < sv->n; ++q) pos[q] = sv->pos[q];
+  return QB200_OK;
+}
+
+int qb200_sv_shard(const qb200_sv* sv, unsigned local_index, unsigned* rank, int* device, void** state, qb200_ctx** ctx) {
+  if (!sv || local_index >= sv->sh.size()) return QB200_ERR_INVALID;
+  const Shard& s = sv->sh[local_index];
+  if (rank) *rank = s.rank;
+  if (device) *device = s.device;
+  if (state) *state = s.buf[sv->cur];
+  if (ctx) *ctx = s.ctx;
+  return QB200_OK;
+}
+
+unsigned qb200_sv_num_local_shards(const qb200_sv* sv) { return sv ? (unsigned) sv->sh.size() : 0; }
+
+int qb200_sv_set_option(qb200_sv* sv, const char* key, int value) {
+  if (!sv || !key) return QB200_ERR_INVALID;
+  if (!std::strcmp(key, "swap_mode")) sv->swap_mode = value;
+  else if (!std::strcmp(key, "reorder")) sv->reorder = value;
+  else if (!std::strcmp(key, "barrier_flags")) {
+    if (sv->mp && !value) return QB200_ERR_INVALID;  // events do not cross processes
+    sv->barrier_flags = value;
+  } else {
+    // anything else is a kernel tuning key of the per-shard contexts (qb200_ctx_set_tuning)
+    for (auto& s : sv->sh) SV_TRY(qb200_ctx_set_tuning(s.ctx, key, value));
+  }
+  return QB200_OK;
+}
+
+int qb200_sv_sync(qb200_sv* sv) { return sv ? sync_all(sv) : QB200_ERR_INVALID; }
+
+uint64_t qb200_sv_launch_count(const qb200_sv* sv) {
+  uint64_t c = 0;
+  if (sv) for (auto& s : sv->sh) c += s.ctx->launches;
+  return c;
+}
+
+int qb200_sv_get_stats(qb200_sv* sv, qb200_sv_stats* out) {
+  if (!sv || !out) return QB200_ERR_INVALID;
+  SV_TRY(timing_collect(sv));
+  out->swaps = sv->stats.swaps;
+  out->local_swap_passes = sv->stats.local_passes;
+  out->gate_passes = sv->stats.gate_passes;
+  out->bytes_sent_per_shard = sv->stats.bytes_sent_per_shard;
+  out->exchange_ms = sv->stats.exchange_ms;
+  return QB200_OK;
+}
+
+int qb200_sv_reset_stats(qb200_sv* sv) {
+  if (!sv) return QB200_ERR_INVALID;
+  SV_TRY(timing_collect(sv));
+  sv->stats = SvStats();
+  return QB200_OK;
+}
+
+// ---- state initialisation ---------------------------------------------------------------------------------------
+int qb200_sv_set_all_zeros(qb200_sv* sv) {
+  if (!sv) return QB200_ERR_INVALID;
+  for (auto& s : sv->sh) SV_TRY(qb200_set_all_zeros(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl));
+  return QB200_OK;
+}
+
+int qb200_sv_set_state_zero(qb200_sv* sv) {
+  if (!sv) return QB200_ERR_INVALID;
+  SV_TRY(qb200_sv_set_all_zeros(sv));
+  // |0...0> is index 0 under every qubit map
+  if (Shard* s = local_shard(sv, 0)) SV_TRY(qb200_set_ampl(s->ctx, sv->dtype, cur_buf(sv, *s), 0, 1.0, 0.0));
+  return QB200_OK;
+}
+
+int qb200_sv_set_state_uniform(qb200_sv* sv) {
+  if (!sv) return QB200_ERR_INVALID;
+  const double v = 1.0 / std::sqrt((double) (uint64_t{1} << sv->n));  // lib/statespace_cuda.h:122
+  for (auto& s : sv->sh) SV_TRY(qb200_bulk_set_ampl(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, 0, 0, v, 0.0, 0));
+  return QB200_OK;
+}
+
+// resets the qubit map to the identity without moving data (only meaningful before the state is (re)initialised)
+int qb200_sv_reset_map(qb200_sv* sv) {
+  if (!sv) return QB200_ERR_INVALID;
+  for (unsigned q = 0; q < sv->n; ++q) sv->pos[q] = q;
+  return QB200_OK;
+}
+
+int qb200_sv_get_ampl(qb200_sv* sv, uint64_t i, double out[2]) {
+  if (!sv || !out || (i >> sv->n)) return QB200_ERR_INVALID;
+  const uint64_t p = to_physical(sv, i);
+  double v[2] = {0, 0};
+  if (Shard* s = local_shard(sv, (unsigned) (p >> sv->nl)))
+    SV_TRY(qb200_get_ampl(s->ctx, sv->dtype, cur_buf(sv, *s), p & ((uint64_t{1} << sv->nl) - 1), v));
+  SV_TRY(sum_over_ranks(sv, v, 2));
+  out[0] = v[0];
+  out[1] = v[1];
+  return QB200_OK;
+}
+
+int qb200_sv_set_ampl(qb200_sv* sv, uint64_t i, double re, double im) {
+  if (!sv || (i >> sv->n)) return QB200_ERR_INVALID;
+  const uint64_t p = to_physical(sv, i);
+  if (Shard* s = local_shard(sv, (unsigned) (p >> sv->nl)))
+    SV_TRY(qb200_set_ampl(s->ctx, sv->dtype, cur_buf(sv, *s), p & ((uint64_t{1} << sv->nl) - 1), re, im));
+  return QB200_OK;
+}
+
+int qb200_sv_bulk_set_ampl(qb200_sv* sv, uint64_t mask, uint64_t bits, double re, double im, int exclude) {
+  if (!sv) return QB200_ERR_INVALID;
+  const uint64_t pm = to_physical(sv, mask), pb = to_physical(sv, bits);
+  const uint64_t lmask = pm & ((uint64_t{1} << sv->nl) - 1), lbits = pb & ((uint64_t{1} << sv->nl) - 1);
+  const uint64_t gmask = pm >> sv->nl, gbits = pb >> sv->nl;
+  for (auto& s : sv->sh) {
+    const bool gok = (s.rank & gmask) == gbits;
+    if (gok) SV_TRY(qb200_bulk_set_ampl(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, lmask, lbits, re, im, exclude));
+    else if (exclude) SV_TRY(qb200_bulk_set_ampl(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, 0, 0, re, im, 0));
+  }
+  return QB200_OK;
+}
+
+// ---- gates ----------------------------------------------------------------------------------------------------------
+int qb200_sv_apply_controlled_gate(qb200_sv* sv, const unsigned* qs, unsigned nq, const unsigned* cqs, unsigned nc,
+                                   uint64_t cvals, const void* matrix) {
+  if (!sv || !matrix || (nq && !qs) || (nc && !cqs)) return QB200_ERR_INVALID;
+  if (nq > kMaxTargets || (nc > 0 && nq > kMaxCtrlTargets)) return QB200_ERR_UNSUPPORTED;
+  if (nq > sv->nl) return QB200_ERR_UNSUPPORTED;  // lib/simulator_custatevecex.h:67-71: a gate must fit a shard
+  SV_TRY(make_local(sv, qs, nq));
+  touch(sv, qs, nq);
+  return local_gate(sv, qs, nq, cqs, nc, cvals, matrix, false, nullptr);
+}
+
+int qb200_sv_apply_gate(qb200_sv* sv, const unsigned* qs, unsigned nq, const void* matrix) {
+  return qb200_sv_apply_controlled_gate(sv, qs, nq, nullptr, 0, 0, matrix);
+}
+
+int qb200_sv_expectation_value(qb200_sv* sv, const unsigned* qs, unsigned nq, const void* matrix, double out[2]) {
+  if (!sv || !out || !matrix || !qs) return QB200_ERR_INVALID;
+  out[0] = out[1] = 0;
+  if (nq > kMaxTargets || nq > sv->nl) return QB200_ERR_UNSUPPORTED;
+  SV_TRY(make_local(sv, qs, nq));
+  double v[2] = {0, 0};
+  SV_TRY(local_gate(sv, qs, nq, nullptr, 0, 0, matrix, true, v));
+  SV_TRY(sum_over_ranks(sv, v, 2));
+  out[0] = v[0];
+  out[1] = v[1];
+  return QB200_OK;
+}
+
+int qb200_sv_swap(qb200_sv* sv, const unsigned* victims, const unsigned* incoming, unsigned k) {
+  if (!sv || !victims || !incoming) return QB200_ERR_INVALID;
+  return exchange(sv, victims, incoming, k);
+}
+
+int qb200_sv_canonicalize(qb200_sv* sv) { return sv ? canonicalize(sv) : QB200_ERR_INVALID; }
+
+int qb200_sv_plan(unsigned num_qubits, unsigned num_global, const qb200_gate* gates, uint64_t count,
+                  const unsigned* global_qubits, int reorder, int64_t* steps, uint64_t capacity, uint64_t* num_steps) {
+  if (!gates && count) return QB200_ERR_INVALID;
+  if (num_qubits > 63 || num_global > num_qubits) return QB200_ERR_INVALID;
+  std::vector<uint64_t> touch_m(count), need(count);
+  for (uint64_t i = 0; i < count; ++i) {
+    uint64_t t = 0, c = 0;
+    for (unsigned j = 0; j < gates[i].num_targets; ++j) {
+      if (gates[i].qs[j] >= num_qubits) return QB200_ERR_INVALID;
+      t |= uint64_t{1} << gates[i].qs[j];
+    }
+    for (unsigned j = 0; j < gates[i].num_controls; ++j) {
+      if (gates[i].cqs[j] >= num_qubits) return QB200_ERR_INVALID;
+      c |= uint64_t{1} << gates[i].cqs[j];
+    }
+    if ((unsigned) __builtin_popcountll(t) > num_qubits - num_global) return QB200_ERR_UNSUPPORTED;
+    touch_m[i] = t | c;
+    need[i] = t;
+  }
+  uint64_t glob = 0;
+  for (unsigned j = 0; j < num_global; ++j)
+    glob |= uint64_t{1} << (global_qubits ? global_qubits[j] : num_qubits - num_global + j);
+  if ((unsigned) __builtin_popcountll(glob) != num_global) return QB200_ERR_INVALID;
+  SwapPlanner planner(num_qubits, num_global, touch_m, need, glob, reorder != 0);
+  const auto plan = planner.Run();
+  // encoding: a gate step is its op index (>= 0); a swap step is -(k) followed by k victims and k incoming qubits
+  uint64_t w = 0;
+  auto put = [&](int64_t v) {
+    if (steps && w < capacity) steps[w] = v;
+    ++w;
+  };
+  for (const auto& s : plan) {
+    if (!s.is_swap) { put((int64_t) s.op); continue; }
+    put(-(int64_t) s.victims.size());
+    for (unsigned q : s.victims) put(q);
+    for (unsigned q : s.incoming) put(q);
+  }
+  if (num_steps) *num_steps = w;
+  return (steps && w > capacity) ? QB200_ERR_INVALID : QB200_OK;
+}
+
+int qb200_sv_run(qb200_sv* sv, const qb200_gate* gates, uint64_t count) {
+  if (!sv || (!gates && count)) return QB200_ERR_INVALID;
+  for (uint64_t i = 0; i < count; ++i) {
+    if (gates[i].num_targets > kMaxTargets || (gates[i].num_controls && gates[i].num_targets > kMaxCtrlTargets))
+      return QB200_ERR_UNSUPPORTED;
+    if (gates[i].num_targets > sv->nl) return QB200_ERR_UNSUPPORTED;
+  }
+  if (sv->g == 0) {
+    for (uint64_t i = 0; i < count; ++i)
+      SV_TRY(local_gate(sv, gates[i].qs, gates[i].num_targets, gates[i].cqs, gates[i].num_controls, gates[i].cvals,
+                        gates[i].matrix, false, nullptr));
+    return QB200_OK;
+  }
+  std::vector<unsigned> glob;
+  for (unsigned t = 0; t < sv->g; ++t) glob.push_back(qubit_at(sv, sv->nl + t));
+  // the schedule depends only on which qubits each gate touches and on the current global set: a circuit that
+  // is run again (trajectories, benchmark steps) reuses it
+  std::vector<uint64_t> key;
+  key.reserve(2 * count + 2);
+  key.push_back(sv->reorder);
+  for (unsigned q : glob) key.push_back(q);
+  for (uint64_t i = 0; i < count; ++i) {
+    uint64_t t = 0, c = 0;
+    for (unsigned j = 0; j < gates[i].num_targets; ++j) t |= uint64_t{1} << (gates[i].qs[j] & 63);
+    for (unsigned j = 0; j < gates[i].num_controls; ++j) c |= uint64_t{1} << (gates[i].cqs[j] & 63);
+    key.push_back(t);
+    key.push_back(c);
+  }
+  if (key != sv->plan_key) {
+    uint64_t need = 0;
+    SV_TRY(qb200_sv_plan(sv->n, sv->g, gates, count, glob.data(), sv->reorder, nullptr, 0, &need));
+    sv->plan_steps.assign(need, 0);
+    sv->plan_key.clear();
+    SV_TRY(qb200_sv_plan(sv->n, sv->g, gates, count, glob.data(), sv->reorder, sv->plan_steps.data(), need, &need));
+    sv->plan_key = key;
+  }
+  const std::vector<int64_t>& steps = sv->plan_steps;
+  const uint64_t need = steps.size();
+  for (uint64_t w = 0; w < need;) {
+    const int64_t v = steps[w++];
+    if (v >= 0) {
+      const qb200_gate& gt = gates[v];
+      touch(sv, gt.qs, gt.num_targets);
+      SV_TRY(local_gate(sv, gt.qs, gt.num_targets, gt.cqs, gt.num_controls, gt.cvals, gt.matrix, false, nullptr));
+    } else {
+      const unsigned k = (unsigned) -v;
+      unsigned vq[kMaxGlobal], iq[kMaxGlobal];
+      for (unsigned j = 0; j < k; ++j) vq[j] = (unsigned) steps[w + j];
+      for (unsigned j = 0; j < k; ++j) iq[j] = (unsigned) steps[w + k + j];
+      w += 2 * k;
+      SV_TRY(exchange(sv, vq, iq, k));
+    }
+  }
+  return QB200_OK;
+}
+
+// ---- reductions ---------------------------------------------------------------------------------------------------
+// out[r] for every rank r (zeros for the shards of other processes, then summed over the ranks)
+static int per_shard_norms(qb200_sv* sv, uint64_t lmask, uint64_t lbits, uint64_t gmask, uint64_t gbits,
+                           std::vector<double>* out) {
+  out->assign(sv->P, 0.0);
+  for (auto& s : sv->sh) SV_TRY(qb200_reduce_batch_begin(s.ctx, 1));
+  int rc = QB200_OK;
+  for (auto& s : sv->sh) {
+    if ((s.rank & gmask) != gbits) continue;
+    double dummy;
+    rc = qb200_masked_norm(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, lmask, lbits, &dummy);
+    if (rc) break;
+  }
+  for (auto& s : sv->sh) {
+    double r[4] = {0, 0, 0, 0};
+    uint32_t cnt = 0;
+    int rc2 = qb200_reduce_batch_end(s.ctx, r, 2, &cnt);
+    if (rc2 && !rc) rc = rc2;
+    if (cnt) (*out)[s.rank] = r[0];
+  }
+  if (rc) return rc;
+  return sum_over_ranks(sv, out->data(), sv->P);
+}
+
+int qb200_sv_norm(qb200_sv* sv, double* out) {
+  if (!sv || !out) return QB200_ERR_INVALID;
+  std::vector<double> v;
+  SV_TRY(per_shard_norms(sv, 0, 0, 0, 0, &v));
+  double t = 0;
+  for (double x : v) t += x;
+  *out = t;
+  return QB200_OK;
+}
+
+static bool same_shape(const qb200_sv* a, const qb200_sv* b) {
+  return a && b && a->n == b->n && a->P == b->P && a->dtype == b->dtype && a->mp == b->mp &&
+         a->sh.size() == b->sh.size();
+}
+
+static int align_maps(qb200_sv* a, qb200_sv* b) {
+  if (a->pos == b->pos) return QB200_OK;
+  SV_TRY(canonicalize(a));
+  return canonicalize(b);
+}
+
+int qb200_sv_inner_product(qb200_sv* a, qb200_sv* b, double out[2]) {
+  if (!out || !same_shape(a, b)) return QB200_ERR_INVALID;
+  SV_TRY(align_maps(a, b));
+  for (auto& s : a->sh) SV_TRY(qb200_reduce_batch_begin(s.ctx, 1));
+  int rc = QB200_OK;
+  for (size_t i = 0; i < a->sh.size() && !rc; ++i) {
+    // b's kernels run on b's streams: order a's read after them
+    DevScope d(a->sh[i].device);
+    cudaEventRecord(b->sh[i].ev, b->sh[i].stream);
+    cudaStreamWaitEvent(a->sh[i].stream, b->sh[i].ev, 0);
+    double dummy[2];
+    rc = qb200_inner_product(a->sh[i].ctx, a->dtype, cur_buf(a, a->sh[i]), cur_buf(b, b->sh[i]), a->nl, dummy);
+  }
+  double v[2] = {0, 0};
+  for (auto& s : a->sh) {
+    double r[4] = {0, 0, 0, 0};
+    uint32_t cnt = 0;
+    int rc2 = qb200_reduce_batch_end(s.ctx, r, 2, &cnt);
+    if (rc2 && !rc) rc = rc2;
+    if (cnt) { v[0] += r[0]; v[1] += r[1]; }
+  }
+  if (rc) return rc;
+  SV_TRY(sum_over_ranks(a, v, 2));
+  out[0] = v[0];
+  out[1] = v[1];
+  return QB200_OK;
+}
+
+int qb200_sv_add(qb200_sv* src, qb200_sv* dest) {
+  if (!same_shape(src, dest)) return QB200_ERR_INVALID;
+  SV_TRY(align_maps(src, dest));
+  for (size_t i = 0; i < src->sh.size(); ++i) {
+    DevScope d(dest->sh[i].device);
+    cudaEventRecord(src->sh[i].ev, src->sh[i].stream);
+    cudaStreamWaitEvent(dest->sh[i].stream, src->sh[i].ev, 0);
+    SV_TRY(qb200_add(dest->sh[i].ctx, dest->dtype, cur_buf(src, src->sh[i]), cur_buf(dest, dest->sh[i]), dest->nl));
+    // ... and src must not be overwritten before the add has read it
+    cudaEventRecord(dest->sh[i].ev, dest->sh[i].stream);
+    cudaStreamWaitEvent(src->sh[i].stream, dest->sh[i].ev, 0);
+  }
+  return QB200_OK;
+}
+
+int qb200_sv_copy(qb200_sv* src, qb200_sv* dest) {
+  if (!same_shape(src, dest)) return QB200_ERR_INVALID;
+  for (size_t i = 0; i < src->sh.size(); ++i) {
+    DevScope d(dest->sh[i].device);
+    cudaEventRecord(src->sh[i].ev, src->sh[i].stream);
+    cudaStreamWaitEvent(dest->sh[i].stream, src->sh[i].ev, 0);
+    if (cudaMemcpyAsync(cur_buf(dest, dest->sh[i]), cur_buf(src, src->sh[i]), shard_bytes(src), cudaMemcpyDeviceToDevice,
+                        dest->sh[i].stream) != cudaSuccess) {
+      (void) cudaGetLastError();
+      return QB200_ERR_CUDA;
+    }
+    cudaEventRecord(dest->sh[i].ev, dest->sh[i].stream);
+    cudaStreamWaitEvent(src->sh[i].stream, dest->sh[i].ev, 0);
+  }
+  dest->pos = src->pos;
+  return sync_all(dest);
+}
+
+int qb200_sv_multiply(qb200_sv* sv, double a) {
+  if (!sv) return QB200_ERR_INVALID;
+  for (auto& s : sv->sh) SV_TRY(qb200_multiply(s.ctx, sv->dtype, a, cur_buf(sv, s), sv->nl));
+  return QB200_OK;
+}
+
+// ---- sampling and measurement (canonical order: same cumulative sums as the unsharded state) --------------------
+int qb200_sv_sample(qb200_sv* sv, const double* sorted_rs, uint64_t num_samples, uint64_t* out) {
+  if (!sv || (num_samples && (!sorted_rs || !out))) return QB200_ERR_INVALID;
+  if (num_samples == 0) return QB200_OK;
+  SV_TRY(canonicalize(sv));
+  std::vector<double> norms;
+  SV_TRY(per_shard_norms(sv, 0, 0, 0, 0, &norms));
+  std::vector<double> res(num_samples, 0.0);
+  double lo = 0;
+  uint64_t first = 0;
+  for (unsigned r = 0; r < sv->P; ++r) {
+    const double hi = lo + norms[r];
+    uint64_t last = first;
+    // the last shard also takes the draws that round-off left beyond the total (lib/statespace_basic.h:227-229)
+    while (last < num_samples && (sorted_rs[last] < hi || r + 1 == sv->P)) ++last;
+    if (last > first) {
+      if (Shard* s = local_shard(sv, r)) {
+        std::vector<double> rs(last - first);
+        for (uint64_t i = first; i < last; ++i) rs[i - first] = sorted_rs[i] - lo;
+        std::vector<uint64_t> idx(last - first);
+        SV_TRY(qb200_sample(s->ctx, sv->dtype, cur_buf(sv, *s), sv->nl, rs.data(), last - first, idx.data()));
+        for (uint64_t i = first; i < last; ++i) res[i] = (double) (idx[i - first] | (uint64_t{r} << sv->nl));
+      }
+    }
+    first = last;
+    lo = hi;
+  }
+  SV_TRY(sum_over_ranks(sv, res.data(), num_samples));  // indices < 2^53 are exact in double
+  for (uint64_t i = 0; i < num_samples; ++i) out[i] = (uint64_t) res[i];
+  return QB200_OK;
+}
+
+uint64_t qb200_sv_partial_norms_count(const qb200_sv* sv) {
+  return sv ? qb200_partial_norms_count(sv->nl) * sv->P : 0;
+}
+
+int qb200_sv_partial_norms(qb200_sv* sv, double* out) {
+  if (!sv || !out) return QB200_ERR_INVALID;
+  SV_TRY(canonicalize(sv));
+  const uint64_t per = qb200_partial_norms_count(sv->nl);
+  std::fill(out, out + per * sv->P, 0.0);
+  for (auto& s : sv->sh) SV_TRY(qb200_partial_norms(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, out + per * s.rank));
+  return sum_over_ranks(sv, out, per * sv->P);
+}
+
+int qb200_sv_find_measured_bits(qb200_sv* sv, uint64_t m, double r, uint64_t mask, uint64_t* out_bits) {
+  if (!sv || !out_bits) return QB200_ERR_INVALID;
+  SV_TRY(canonicalize(sv));
+  const uint64_t per = qb200_partial_norms_count(sv->nl);
+  const unsigned rank = (unsigned) (m / per);
+  if (rank >= sv->P) return QB200_ERR_INVALID;
+  double v = 0;
+  if (Shard* s = local_shard(sv, rank)) {
+    uint64_t bits = 0;
+    SV_TRY(qb200_find_measured_bits(s->ctx, sv->dtype, cur_buf(sv, *s), sv->nl, m % per, r,
+                                    mask & ((uint64_t{1} << sv->nl) - 1), &bits));
+    v = (double) (bits | ((uint64_t{rank} << sv->nl) & mask));
+  }
+  SV_TRY(sum_over_ranks(sv, &v, 1));
+  *out_bits = (uint64_t) v;
+  return QB200_OK;
+}
+
+int qb200_sv_collapse(qb200_sv* sv, uint64_t mask, uint64_t bits, double* out_norm) {
+  if (!sv) return QB200_ERR_INVALID;
+  const uint64_t pm = to_physical(sv, mask), pb = to_physical(sv, bits);
+  const uint64_t lmask = pm & ((uint64_t{1} << sv->nl) - 1), lbits = pb & ((uint64_t{1} << sv->nl) - 1);
+  const uint64_t gmask = pm >> sv->nl, gbits = pb >> sv->nl;
+  std::vector<double> norms;
+  SV_TRY(per_shard_norms(sv, lmask, lbits, gmask, gbits, &norms));
+  double t = 0;
+  for (double x : norms) t += x;
+  if (out_norm) *out_norm = t;
+  const double renorm = 1.0 / std::sqrt(t);  // lib/statespace_cuda.h:319
+  for (auto& s : sv->sh) {
+    if ((s.rank & gmask) == gbits) SV_TRY(qb200_collapse_scaled(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, lmask, lbits, renorm));
+    else SV_TRY(qb200_set_all_zeros(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl));
+  }
+  return QB200_OK;
+}
+
+// ---- host transfers (canonical order; a multi-process state moves only this process's shard, at its offset) -----
+int qb200_sv_copy_to_host(qb200_sv* sv, void* host) {
+  if (!sv || !host) return QB200_ERR_INVALID;
+  SV_TRY(canonicalize(sv));
+  const size_t bytes = shard_bytes(sv);
+  for (auto& s : sv->sh) {
+    DevScope d(s.device);
+    SV_CUDA(sv, cudaMemcpyAsync((char*) host + bytes * s.rank, cur_buf(sv, s), bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  return sync_all(sv);
+}
+
+int qb200_sv_copy_from_host(qb200_sv* sv, const void* host) {
+  if (!sv || !host) return QB200_ERR_INVALID;
+  for (unsigned q = 0; q < sv->n; ++q) sv->pos[q] = q;
+  const size_t bytes = shard_bytes(sv);
+  for (auto& s : sv->sh) {
+    DevScope d(s.device);
+    SV_CUDA(sv, cudaMemcpyAsync(cur_buf(sv, s), (const char*) host + bytes * s.rank, bytes, cudaMemcpyHostToDevice, s.stream));
+  }
+  return sync_all(sv);
+}
+
+}  // extern "C"

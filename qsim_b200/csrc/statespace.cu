@@ -386,6 +386,9 @@ int sample(qb200_ctx* ctx, const FP* st, unsigned n, const double* sorted_rs, ui
 
 template <typename FP>
 int collapse(qb200_ctx* ctx, FP* st, unsigned n, uint64_t mask, uint64_t bits, double* out_norm) {
+  // the masked norm is needed on the host NOW: not available inside qb200_reduce_batch_begin/end, where every
+  // reduction of the context is deferred (the state would be scaled by NaN)
+  if (ctx && ctx->batching) return QB200_ERR_INVALID;
   double r[2];
   int rc = reduce<FP, 0>(ctx, st, st, n, mask, bits, r);
   if (rc) return rc;
@@ -543,6 +546,24 @@ int qb200_collapse(qb200_ctx* ctx, int dtype, void* state, unsigned n, uint64_t 
                    double* out_norm) {
   QB_DISPATCH(dtype, collapse<FP>(ctx, (FP*) state, n, mask, bits, out_norm),
               collapse<FP>(ctx, (FP*) state, n, mask, bits, out_norm));
+}
+
+int qb200_masked_norm(qb200_ctx* ctx, int dtype, const void* state, unsigned n, uint64_t mask, uint64_t bits,
+                      double* out) {
+  if (!out) return QB200_ERR_INVALID;
+  double r[2] = {0, 0};
+  int rc;
+  if (dtype == QB200_F32) rc = reduce<float, 0>(ctx, (const float*) state, (const float*) state, n, mask, bits, r);
+  else if (dtype == QB200_F64) rc = reduce<double, 0>(ctx, (const double*) state, (const double*) state, n, mask, bits, r);
+  else rc = QB200_ERR_INVALID;
+  *out = r[0];
+  return rc;
+}
+
+int qb200_collapse_scaled(qb200_ctx* ctx, int dtype, void* state, unsigned n, uint64_t mask, uint64_t bits,
+                          double renorm) {
+  QB_DISPATCH(dtype, (launch_map<FP, true>(ctx, (FP*) state, n, FCollapse<FP>{mask, bits, (FP) renorm})),
+              (launch_map<FP, true>(ctx, (FP*) state, n, FCollapse<FP>{mask, bits, (FP) renorm})));
 }
 
 int qb200_internal_to_normal_order(qb200_ctx* ctx, int, void*, unsigned) {

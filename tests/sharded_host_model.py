@@ -1,5 +1,8 @@
-"""State sharded over 2^g ranks by *global qubits* (one process per GPU,
-torch.distributed for the plumbing, NCCL over NVLink on the GPU box).
+"""TEST-SIDE host model of a state sharded over 2^g ranks by *global qubits* (torch.distributed over gloo,
+shards driven by the CPU checker).  The product is csrc/sharded.cu behind the C ABI (qb200_sv_*); this file
+restates its host logic -- qubit map, matrix re-indexing, global controls, the index arithmetic of both
+exchange kernels -- so that world_size 2/4 CPU tests can replay the schedules of the library's planner
+(qb200_sv_plan) and compare with an unsharded run.  Round 1 shipped this as qsim_b200/sharded.py.
 
 Reference precedent: the cuStateVecEx backend's wire ordering + index-bit swaps
 (lib/vectorspace_custatevecex.h:163-177, lib/simulator_custatevecex.h:147-196,
@@ -306,6 +309,8 @@ class ShardedSimulator:
         import time
         k = len(victims)
         assert k == len(incoming) and k >= 1
+        if getattr(self.engine, "remap", False) and self.dist is not None and self.world > 1:
+            return self._swap_remap(list(victims), list(incoming), before_op)
         if getattr(self.engine, "p2p", False) and self.dist is not None and self.world > 1:
             return self._swap_p2p(victims, incoming, before_op)
         top = list(range(self.n_local - k, self.n_local))
@@ -366,6 +371,39 @@ class ShardedSimulator:
         self.stats.swaps += 1
         self.stats.bytes_sent += sent
         self.stats.detail.append((before_op, k, sent))
+
+    def _swap_remap(self, victims, incoming, before_op):
+        """out-of-place exchange, the index arithmetic of k_remap_push (csrc/sharded.cu): the victims' bits are
+        squeezed out of the local index (order of the rest kept), every shard lands in slice `my` of each
+        destination, incoming qubit j ends on local bit n_local - k + j."""
+        k = len(victims)
+        victims = sorted(victims, key=lambda q: self.pos[q])
+        lbits = [self.pos[v] for v in victims]
+        gbits = [self.pos[q] - self.n_local for q in incoming]
+        my = sum(((self.rank >> gb) & 1) << j for j, gb in enumerate(gbits))
+        dst_ranks = [self._peer(gbits, b) for b in range(1 << k)]
+        self.engine.remap_push(dst_ranks, k, lbits, my)
+        for q in range(self.n):
+            p = self.pos[q]
+            if p >= self.n_local or q in victims:
+                continue
+            self.pos[q] = p - sum(1 for b in lbits if b < p)
+        for j in range(k):
+            self.pos[victims[j]] = self.n_local + gbits[j]
+            self.pos[incoming[j]] = self.n_local - k + j
+        sent = ((2 << self.n_local) >> k) * ((1 << k) - 1) * self.engine.element_size
+        self.stats.swaps += 1
+        self.stats.bytes_sent += sent
+        self.stats.detail.append((before_op, k, sent))
+
+    def run_schedule(self, ops, schedule):
+        """schedule: qsim_b200.sv.plan() output -- ("gate", i) / ("swap", victims, incoming)."""
+        for step in schedule:
+            if step[0] == "gate":
+                op = ops[step[1]]
+                self._local_gate(list(op.qubits), list(op.controls), op.cvals, op.matrix)
+            else:
+                self.swap(step[1], step[2])
 
     def _peer(self, gbits, b):
         r = self.rank

@@ -1,7 +1,8 @@
 """Sharded state (global-qubit swaps as grouped send/recv) on CPU: world_size 2 and 4
 over the gloo backend, local shards driven by the CPU oracle (tests only).  Checks the
-host logic of qsim_b200/sharded.py -- planner, matrix re-indexing, qubit map, exchange
-indexing, global controls -- against an unsharded oracle run of the same circuit."""
+host logic of the sharded state -- the library's swap planner (qb200_sv_plan, host-only C++), matrix
+re-indexing, qubit map, the index arithmetic of both exchange kernels, global controls -- replayed by
+tests/sharded_host_model.py against an unsharded oracle run of the same circuit."""
 import os
 import socket
 import sys
@@ -12,7 +13,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from qsim_b200.sharded import ShardedSimulator, SwapStep, plan_swaps, reindex_matrix  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from sharded_host_model import ShardedSimulator, SwapStep, plan_swaps, reindex_matrix  # noqa: E402
 from qsim_b200.trace import TraceOp, read_trace  # noqa: E402
 
 
@@ -105,6 +107,45 @@ class PeerOracleEngine(OracleEngine):
             self.np[sel] = inc.numpy().view(np.complex64)
 
 
+class RemapOracleEngine(PeerOracleEngine):
+    """Emulates the out-of-place push exchange (k_remap_push, csrc/sharded.cu) over gloo."""
+    remap = True
+
+    def remap_push(self, dst_ranks, k, lbits, my):
+        import torch
+        nl = self.n_local
+        idx = np.arange(1 << nl, dtype=np.int64)
+        v = np.zeros_like(idx)
+        rest = idx.copy()
+        for j in range(k - 1, -1, -1):
+            b = lbits[j]
+            v |= ((rest >> b) & 1) << j
+            rest = ((rest >> (b + 1)) << b) | (rest & ((1 << b) - 1))
+        dest_idx = rest | (my << (nl - k))
+        new = np.zeros_like(self.np)
+        reqs, incoming = [], []
+        for val in range(1 << k):
+            sel = np.nonzero(v == val)[0]
+            order = np.argsort(dest_idx[sel])
+            payload = np.ascontiguousarray(self.np[sel][order])
+            where = dest_idx[sel][order]            # the slice `my` of the destination, ascending
+            if dst_ranks[val] == self.dist.get_rank():
+                new[where] = payload
+                continue
+            out = torch.from_numpy(payload.view(np.float32).copy())
+            inc = torch.empty_like(out)
+            reqs.append(self.dist.isend(out, dst=dst_ranks[val]))
+            reqs.append(self.dist.irecv(inc, src=dst_ranks[val]))
+            incoming.append((val, inc))
+        for r in reqs:
+            r.wait()
+        for val, inc in incoming:
+            # the sender whose exchanged rank bits equal `val` fills slice `val` of my new buffer
+            lo = val << (nl - k)
+            new[lo:lo + (1 << (nl - k))] = inc.numpy().view(np.complex64)
+        self.np[:] = new
+
+
 def random_ops(n, count, seed, max_local):
     rs = np.random.RandomState(seed)
     ops = []
@@ -145,17 +186,21 @@ def oracle_full(n, ops):
     return st
 
 
-def _worker(rank, world, port, n, ops, transfer_scalars, out_dir, p2p=False):
+def _worker(rank, world, port, n, ops, transfer_scalars, out_dir, p2p=False, schedule=None):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         g = world.bit_length() - 1
-        eng = PeerOracleEngine(n - g, dist) if p2p else OracleEngine(n - g)
+        eng = RemapOracleEngine(n - g, dist) if p2p == "remap" else PeerOracleEngine(n - g, dist) if p2p else OracleEngine(n - g)
         sim = ShardedSimulator(n, eng, dist=dist, rank=rank, world_size=world, transfer_scalars=transfer_scalars)
         sim.set_state_zero()
-        plan = sim.run(ops)
+        if schedule is not None:
+            sim.run_schedule(ops, schedule)
+            plan = [s for s in schedule if s[0] == "swap"]
+        else:
+            plan = sim.run(ops)
         norm = sim.norm()
         amp5 = sim.get_ampl(5)
         swaps, sent, lsp = sim.stats.swaps, sim.stats.bytes_sent, sim.stats.local_swap_passes
@@ -177,9 +222,9 @@ def free_port():
     return p
 
 
-def run_sharded(world, n, ops, tmp_path, transfer_scalars=1 << 28, p2p=False):
+def run_sharded(world, n, ops, tmp_path, transfer_scalars=1 << 28, p2p=False, schedule=None):
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, free_port(), n, ops, transfer_scalars, str(tmp_path), p2p), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, free_port(), n, ops, transfer_scalars, str(tmp_path), p2p, schedule), nprocs=world, join=True)
     g = world.bit_length() - 1
     n_local = n - g
     full = np.zeros(1 << n, np.complex64)
@@ -237,6 +282,67 @@ def test_sharded_peer_memory_swap_path(world, tmp_path):
     assert int(res[0]["swaps"]) >= 2 and int(res[0]["swaps"]) == int(res[0]["nplan"])
     assert int(res[0]["local_swap_passes"]) >= 1  # random victims do land on the low bits
     check_expectations(n, want, res)
+
+
+@pytest.mark.parametrize("world,mode", [(2, "remap"), (4, "remap"), (4, True)])
+def test_library_schedule_replayed_over_gloo(world, mode, tmp_path):
+    """The schedule of the library's planner (reordered gates + exchanges, qb200_sv_plan through the C ABI)
+    replayed on oracle-driven shards over gloo with the index arithmetic of the push exchange (remap) and of
+    the in-place exchange: the sharded result equals the in-order unsharded run."""
+    from qsim_b200 import sv
+    n = 10
+    g = world.bit_length() - 1
+    ops = random_ops(n, 60, seed=20 + world, max_local=n - g)
+    want = oracle_full(n, ops)
+    schedule = sv.plan(n, g, ops, reorder=True)
+    assert sorted(s[1] for s in schedule if s[0] == "gate") == list(range(len(ops)))
+    got, res = run_sharded(world, n, ops, tmp_path, p2p=mode, schedule=schedule)
+    assert np.abs(got - want).max() < 3e-6
+    assert int(res[0]["swaps"]) == sum(1 for s in schedule if s[0] == "swap") >= 1
+    check_expectations(n, want, res)
+
+
+def check_schedule(n, g, ops, schedule, glob=None):
+    """every gate exactly once, per-qubit program order kept, targets local when the gate runs"""
+    glob = set(range(n - g, n)) if glob is None else set(glob)
+    last = {}
+    seen = []
+    for step in schedule:
+        if step[0] == "swap":
+            assert len(step[1]) == len(step[2]) >= 1
+            assert set(step[2]) <= glob and not (set(step[1]) & glob)
+            glob = (glob - set(step[2])) | set(step[1])
+            continue
+        i = step[1]
+        seen.append(i)
+        assert not (set(ops[i].qubits) & glob), "target on a global qubit"
+        for q in list(ops[i].qubits) + list(ops[i].controls):
+            assert last.get(q, -1) < i, "per-qubit order violated"
+            last[q] = i
+    assert sorted(seen) == list(range(len(ops)))
+    return sum(1 - 2.0 ** -len(s[1]) for s in schedule if s[0] == "swap")
+
+
+def test_library_planner_on_the_benchmark_circuits():
+    from qsim_b200 import sv
+    # (qubits, global qubits) -> exchanged bytes in shards, in-order and reordered: the reordering planner
+    # needs 1-2 exchanges where the in-order one needs 3-4
+    for n, g, max_cost in ((31, 1, 0.5), (32, 2, 0.75), (33, 3, 1.375), (36, 2, 0.75), (37, 3, 1.375)):
+        _, ops = read_trace(os.path.join(ROOT, "tests", "golden", f"rqc_q{n}_d20_f4.trace"))
+        c_in = check_schedule(n, g, ops, sv.plan(n, g, ops, reorder=False))
+        c_re = check_schedule(n, g, ops, sv.plan(n, g, ops, reorder=True))
+        assert c_re <= max_cost + 1e-9 and c_re < c_in
+        # in-order schedules keep the program order
+        assert [s[1] for s in sv.plan(n, g, ops, reorder=False) if s[0] == "gate"] == list(range(len(ops)))
+    # nothing to do without global qubits; a given initial global set is honoured
+    _, ops = read_trace(os.path.join(ROOT, "tests", "golden", "rqc_q20_d20_f4.trace"))
+    assert all(s[0] == "gate" for s in sv.plan(20, 0, ops))
+    check_schedule(20, 2, ops, sv.plan(20, 2, ops, global_qubits=[3, 7]), glob=[3, 7])
+    # controls may stay global: a controlled gate whose control is global needs no exchange
+    from qsim_b200.trace import TraceOp
+    x = np.array([0, 0, 1, 0, 1, 0, 0, 0], np.float32)
+    sched = sv.plan(6, 1, [TraceOp([0], [5], 1, x), TraceOp([1], [], 0, x)])
+    assert all(s[0] == "gate" for s in sched)
 
 
 def test_sharded_rqc_trace_world2(tmp_path):
