@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 
 TRACE = os.path.join(ROOT, "tests", "golden", "q30_d20_f4.trace")
 METRIC = "rqc_q30_d20_f4_fused_gate_hbm_gbs"
+WORKLOAD = ("circuits/circuit_q30 depth 20, max_fused_size 4: 41 fused-gate passes (reference parser + fuser output, "
+            "tests/golden/q30_d20_f4.trace) on a 2^30-amplitude fp32 state (8 GiB)")
 
 
 # stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner,
@@ -128,6 +130,44 @@ def cpu_reference_run(ops, n, min_seconds=10.0, max_gates=None, threads=None):
             "est_full_circuit_s": t_total / done * len(ops)}
 
 
+def gpu_reference_baseline(fused=4, runs=2):
+    """The reference's OWN CUDA backend (apps/qsim_base_cuda.cu recompiled for sm_100a by oracle/Makefile,
+    oracle/_ref/qsim_base_cuda_ref) on the same GPU and circuit: the GPU kernel-to-beat of SURVEY 2.3.  Its
+    own "-v 2" clock ("simu time": the fused-gate loop bracketed by device synchronisation)."""
+    import re
+    exe = os.path.join(ROOT, "oracle", "_ref", "qsim_base_cuda_ref")
+    circ = os.path.join(ROOT, "oracle", "_ref", "circuits", "circuit_q30")
+    if not (os.path.exists(exe) and os.path.exists(circ)):
+        return {"kind": "unavailable", "why": "oracle/_ref/qsim_base_cuda_ref not built (reference tree absent at build time)"}
+    times, amp0 = [], None
+    try:
+        for _ in range(runs + 1):
+            p = subprocess.run([exe, "-c", circ, "-d", "20", "-f", str(fused), "-v", "2"], capture_output=True, text=True, timeout=300)
+            m = re.search(r"simu time is ([0-9.eE+-]+) seconds", p.stdout + p.stderr)
+            a = re.search(r"^000:\s+(\S+)\s+(\S+)", p.stdout, flags=re.M)
+            if p.returncode != 0 or not m:
+                return {"kind": "unavailable", "why": (p.stderr or p.stdout)[-300:]}
+            times.append(float(m.group(1)))
+            amp0 = [float(a.group(1)), float(a.group(2))] if a else None
+    except Exception as e:
+        return {"kind": "unavailable", "why": str(e)}
+    best = min(times[1:])   # first run pays context creation inside the process but outside "simu time"; keep it out anyway
+    return {"kind": "reference CUDA backend (lib/simulator_cuda.h) recompiled for sm_100a, same GPU, same circuit, -f %d" % fused,
+            "ms_per_circuit": best * 1e3, "runs_ms": [t * 1e3 for t in times], "amp0": amp0,
+            "value": 41 * 16.0 * (1 << 30) / best / 1e9 if fused == 4 else None, "unit": "GB/s"}
+
+
+Q30_KNOWN = {0: (1.4871957e-5, 2.8161678e-5), 1: (1.8767701e-5, 7.3190154e-6),
+             2: (-1.1130518e-5, 1.6207156e-5), 7: (-1.622395e-5, 3.5199686e-5)}   # reference qsim_base, BASELINE.md 4
+
+
+def parity_block(get_ampl, norm, known, tol, what):
+    errs = [abs(get_ampl(i) - complex(*v)) for i, v in known.items()]
+    ok = bool(max(errs) <= tol and abs(norm - 1.0) < 1e-4)
+    return {"ok": ok, "amplitudes_checked": len(errs), "max_abs_err": float(max(errs)), "tolerance": tol,
+            "norm": norm, "against": what}
+
+
 def run_reference_arm(args, rank):
     import qsim_b200
     if rank != 0:
@@ -135,8 +175,9 @@ def run_reference_arm(args, rank):
     n, ops = qsim_b200.read_trace(TRACE)
     per_step = []
     res = None
+    # a step = ALL fused gates of the circuit (same config as the GPU arm); ~5 s per step on 16-32 host cores
     for it in range(args.warmup + args.steps):
-        res = cpu_reference_run(ops, n, min_seconds=6.0, max_gates=8)
+        res = cpu_reference_run(ops, n, min_seconds=1e9)
         if it >= args.warmup:
             per_step.append(res)
     val = float(np.mean([r["value"] for r in per_step]))
@@ -145,33 +186,37 @@ def run_reference_arm(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "circuits/circuit_q30 depth 20, max_fused_size 4 (41 fused gates), fp32, CPU reference path",
-                       "l2": "state (8 GiB) far larger than any cache"},
+            "config": {"workload": WORKLOAD, "l2": "state (8 GiB) far larger than any cache",
+                       "arm": "the reference's own CPU path (SimulatorAVX512/AVX via oracle/_ref, all host cores), every one of "
+                              "the 41 fused gates per step"},
             "cpu_baseline": res,
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
 def run_sharded(args, rank, world, local_rank, dist):
-    """N > 1: weak scaling.  One 2^30-amplitude shard (8 GiB) per GPU, n = 30 + log2(N)
-    qubits, circuit built like circuit_q30 by tools/gen_rqc.py and fused by the reference
-    fuser (tests/golden/rqc_q<n>_d20_f4.trace).  Gates on global qubits trigger
-    local<->global swaps = grouped NCCL send/recv over NVLink (qsim_b200/sharded.py)."""
+    """N > 1: weak scaling.  One 2^30-amplitude shard (8 GiB) per GPU, n = 30 + log2(N) qubits, circuit built like
+    circuit_q30 by tools/gen_rqc.py and fused by the reference fuser (tests/golden/rqc_q<n>_d20_f4.trace).  The
+    state is a multi-process qb200_sv (csrc/sharded.cu through qsim_b200/sv.py): the library plans the
+    local<->global exchanges over the fused-gate list and runs them as one push kernel per GPU over NVLink peer
+    memory; torch.distributed only carries the three host-side collectives of qb200_comm."""
     import torch
     import qsim_b200
-    from qsim_b200.sharded import B200Engine, ShardedSimulator, plan_swaps
+    from qsim_b200 import _lib
+    from qsim_b200.sv import ShardedStateB200, pack_gates
 
     g = world.bit_length() - 1
     n = args.shard_qubits + g
     trace = os.path.join(ROOT, "tests", "golden", f"rqc_q{n}_d20_f4.trace")
     nq, ops = qsim_b200.read_trace(trace)
     assert nq == n
-    p2p = os.environ.get("QB200_P2P", "1") == "1"   # 0 = staged NCCL send/recv exchange
-    eng = B200Engine(n - g, local_rank, p2p=p2p)
-    if p2p:
-        eng.connect_peers(dist, rank, world)
-    sim = ShardedSimulator(n, eng, dist=dist, rank=rank, world_size=world, transfer_scalars=1 << 28)
-    opq = [list(o.qubits) + list(o.controls) for o in ops]
+    sv = ShardedStateB200.multi_process(dist, n, local_rank)
+    for kv in args.tune:
+        key, val = kv.split("=")
+        sv.set_option(key, int(val))
+    packed = pack_gates(ops)
+    lib = _lib.load()
+    ctx0 = sv.shards()[0][3]
 
     def barrier():
         torch.cuda.synchronize()
@@ -179,81 +224,102 @@ def run_sharded(args, rank, world, local_rank, dist):
         torch.cuda.synchronize()
 
     def one_run():
-        sim.pos = list(range(n))
-        sim.set_state_zero()
-        sim.run(ops, plan_swaps(opq, n, g))
+        sv.SetStateZero(reset_map=True)
+        sv.Run(packed=packed)
 
     for _ in range(max(args.warmup, 3)):
         one_run()
     barrier()
-    sim.reset_stats()
+    sv.reset_stats()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = eng.sim.launch_count()
-    ev = []
+    l0 = sv.launch_count()
+    dev_ms = 0.0
+    ms = C_float()
     for _ in range(args.steps):
-        sim.pos = list(range(n))
-        sim.set_state_zero()
-        torch.cuda.synchronize()
-        e0 = eng.event()
-        sim.run(ops, plan_swaps(opq, n, g))
-        ev.append((e0, eng.event()))
+        sv.SetStateZero(reset_map=True)
+        barrier()
+        lib.qb200_timer_start(ctx0)
+        sv.Run(packed=packed)
+        lib.qb200_timer_stop_ms(ctx0, ms)
+        dev_ms += float(ms.value)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    launches = eng.sim.launch_count() - l0
-    dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
-    exch_ms = sim.exchange_device_ms()
-    t = torch.tensor([dev_ms, exch_ms], device="cuda", dtype=torch.float64)
+    launches = sv.launch_count() - l0
+    stats = sv.stats()
+    t = torch.tensor([dev_ms, stats["exchange_ms"]], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, exch_ms = float(t[0].item()), float(t[1].item())
     ms_per_step = dev_ms / args.steps
     total_bytes = len(ops) * 16.0 * (1 << n)
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
-    import copy
-    stats = copy.deepcopy(sim.stats)
 
+    # ---- end to end from host buffers (wall clock): plan (cached after the first call) + gates + 8 amplitudes + norm
     e2e_ms = []
+    amps, nrm = None, None
     for it in range(1 + args.steps):
         barrier()
         t0 = time.perf_counter()
         one_run()
-        amps = [sim.get_ampl(i) for i in range(8)]
-        nrm = sim.norm()
+        amps = [sv.GetAmpl(i) for i in range(8)]
+        nrm = sv.Norm()
         torch.cuda.synchronize()
         if it >= 1:
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
     t = torch.tensor([float(np.mean(e2e_ms))], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_step = float(t.item())
+
+    # ---- parity: 64 amplitudes + norm against the single-GPU goldens (tools/make_rqc_goldens.py) ----
+    parity = {"ok": False, "why": "no golden for this circuit"}
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "rqc_amplitudes.json")) as f:
+            gold = json.load(f).get(f"rqc_q{n}_d20_f4")
+        if gold and args.shard_qubits == 30:
+            known = {int(i): tuple(a) for i, a in zip(gold["indices"], gold["amplitudes"])}
+            parity = parity_block(sv.GetAmpl, nrm, known, 5e-8,
+                                  "tests/golden/rqc_amplitudes.json: the same circuit on ONE GPU through the single-GPU path "
+                                  "(q31 also equal to the reference AVX-512 simulator to 1e-10)")
+            parity["golden_norm"] = gold["norm"]
+    except Exception as e:
+        parity = {"ok": False, "why": str(e)}
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        sent = stats.bytes_sent / args.steps
-        swaps = stats.swaps // args.steps
+        swaps = int(stats["swaps"]) // args.steps
+        sent = stats["bytes_sent_per_shard"] / args.steps
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"rqc_q{n} depth 20 (tools/gen_rqc.py, circuit_q30 rules), max_fused_size 4: {len(ops)} fused-gate "
                                        f"passes on a 2^{n}-amplitude fp32 state sharded over {world} GPUs ({8 << (n - g - 30)} GiB shard each)",
                            "l2": f"shard ({8 << (n - g - 30)} GiB) is far larger than L2",
-                           "multi_gpu": f"global-qubit sharding, {swaps} local<->global swaps per circuit ("
-                                        + ("one in-place kernel per GPU over NVLink peer memory" if p2p else "grouped NCCL send/recv, staged")
-                                        + f"), {stats.local_swap_passes // args.steps} local SWAP passes",
+                           "multi_gpu": f"global-qubit sharding behind the C ABI (qb200_sv_*): {swaps} local<->global exchanges per circuit "
+                                        f"planned over the fused-gate list with commuting gates reordered (csrc/sv_plan.h), each ONE push "
+                                        f"kernel per GPU over NVLink peer memory; {int(stats['local_swap_passes']) // args.steps} local SWAP passes",
                            "wall_time_s_per_circuit": ms_per_step * 1e-3},
                 "roofline": {"bound": "hbm", "achieved": value / world, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
                              "frac": value / world / float(peaks["hbm_gbs"]), "traffic": None,
-                             "note": "per-GPU algorithmic gate bytes over the whole step (swap time included)",
+                             "note": "per-GPU algorithmic gate bytes over the whole step (exchange time included)",
                              "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})"},
                 "swap": {"swaps_per_circuit": swaps, "bytes_sent_per_rank_per_circuit": sent,
                          "exchange_ms_per_circuit": exch_ms / args.steps,
                          "nvlink_GBps_per_direction": sent / (exch_ms / args.steps * 1e-3) / 1e9 if exch_ms > 0 else None,
-                         "nvlink_peak_GBps_per_direction": 900.0, "detail_first_circuit": stats.detail[:swaps]},
+                         "nvlink_peak_GBps_per_direction": 900.0},
+                "parity": parity,
                 "cpu_baseline": None,
                 "e2e": {"value": total_bytes / (e2e_step * 1e-3) / 1e9, "unit": "GB/s",
                         "h2d_bytes_per_step": sum(op.matrix.nbytes for op in ops), "d2h_bytes_per_step": 72,
                         "ms_per_step": e2e_step, "amp0": [amps[0].real, amps[0].imag], "norm": nrm},
                 "gpu_launches": int(launches), "clocks": clocks}
         emit(line)
+    sv.close()
+    return parity.get("ok", False)
+
+
+def C_float():
+    import ctypes
+    return ctypes.c_float()
 
 
 def main():
@@ -282,16 +348,18 @@ def main():
     import qsim_b200
 
     torch.cuda.set_device(local_rank)
-    # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO prints a banner there)
-    os.environ["NCCL_DEBUG"] = os.environ.get("QB200_NCCL_DEBUG", "WARN")
+    # NCCL_DEBUG is left as the caller set it: fd 1 already points at stderr (top of this file), so INFO lines
+    # cannot reach the JSON line
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     if world > 1:
-        run_sharded(args, rank, world, local_rank, dist)
+        ok = run_sharded(args, rank, world, local_rank, dist)
         dist.destroy_process_group()
+        if not ok:
+            raise SystemExit("parity check of the sharded state FAILED (see the parity block of the JSON line)")
         return
 
     n, ops = qsim_b200.read_trace(args.trace)
@@ -372,29 +440,25 @@ def main():
         e2e_step = float(t.item())
     e2e_value = total_bytes / (e2e_step * 1e-3) / 1e9
 
-    # ---- per-launch durations, grouped by the kernel the dispatcher picks (gate_launch.cuh) ----
+    # ---- per-launch durations, grouped by the kernel the dispatcher picked (named by the library itself:
+    # qb200_last_kernel_name, set in gate_launch.cuh where the choice is made) ----
     ss.SetStateZero(st)
     per_gate = []
     for op in ops:
         sim.timer_start()
         sim.ApplyGate(op.qubits, op.matrix, st)
-        per_gate.append((len(op.qubits), list(op.qubits), sim.timer_stop_ms()))
-    tc_off = any(kv.replace(" ", "") == "tc=0" for kv in args.tune)
+        per_gate.append((len(op.qubits), list(op.qubits), sim.timer_stop_ms(), sim.last_kernel_name()))
+    kind = {"k_gate_tca": "tcgen05 3xTF32, A in TMEM", "k_gate_tc": "tcgen05 3xTF32, operands in smem",
+            "k_gate_tcx": "tcgen05 3xTF32, A in TMEM", "k_gate_tile": "FFMA2, warp tile",
+            "k_gate_pipe": "FFMA2, cp.async ring", "k_gate_reg": "FFMA2, registers", "k_gate_big": "FFMA2, row blocks",
+            "k_gate_tcl": "tcgen05 3xTF32, low targets staged through shared memory"}
 
-    def kernel_class(g, qs):
-        low_t = qs[1] if g >= 2 and qs[0] == 0 else (qs[0] if g else 0)
-        if g == 5:
-            return "k_gate_big<5> (FFMA2)" if tc_off else "k_gate_tca<5> (tcgen05 3xTF32, A in TMEM)"
-        if g == 4:
-            on_tc = qs[0] >= 4 or qs[0] == 2 or (qs[0] == 3 and qs[1] > 4) or (qs[0] == 0 and not (qs[1] == 1 and qs[2] == 2))
-            if not tc_off and on_tc:  # the dispatcher's per-layout rule (gate_launch.cuh)
-                return "k_gate_tca<4> (tcgen05 3xTF32, A in TMEM)"
-            return "k_gate_tile<4> (FFMA2, warp tile)" if qs[0] <= 2 else "k_gate_pipe<4> (FFMA2, cp.async ring)"
-        return f"k_gate_reg<{g}> (FFMA2)" if g < 6 else "k_gate_big<6> (FFMA2)"
+    def kernel_class(g, qs, name):
+        return f"{name} ({kind.get(name.split('<')[0], 'generic')})"
 
     classes = {}
-    for g, qs, ms in per_gate:
-        classes.setdefault(kernel_class(g, qs), []).append(ms)
+    for g, qs, ms, name in per_gate:
+        classes.setdefault(kernel_class(g, qs, name), []).append(ms)
     total_ms = float(np.sum([p[2] for p in per_gate]))
     kernels = {k: {"launches": len(v), "avg_ms": float(np.mean(v)), "GBps": pass_bytes / (float(np.mean(v)) * 1e-3) / 1e9,
                    "share_of_step": float(np.sum(v)) / total_ms} for k, v in classes.items()}
@@ -408,7 +472,7 @@ def main():
     try:
         with open(os.path.join(ROOT, "profiles", "r01_ncu_g4_traffic.json")) as f:
             tj = json.load(f)
-        key = next(k for k in tj["kernels"] if dom.startswith(k.split("<")[0]) and k.split("<")[1][0] == dom.split("<")[1][0])
+        key = next(k for k in tj["kernels"] if dom.startswith(k.split("<")[0] + "<") and k.split("<")[1][0] == dom.split("<")[1][0])
         k = tj["kernels"][key]
         traffic = (k["dram_bytes_read"] + k["dram_bytes_write"]) * (amps / float(1 << 30))
         traffic_src = f"profiles/r01_ncu_g4_traffic.json [{key}] (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
@@ -426,19 +490,48 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:
-                cpu = cpu_reference_run(ops, n, min_seconds=10.0)
+                cpu = cpu_reference_run(ops, n, min_seconds=1e9)   # the whole circuit, like the GPU arm
             except Exception as e:  # keep the bench line even if the host lacks RAM for the sample
                 cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+        parity = parity_block(lambda i: amp_out[i] if i < 8 else ss.GetAmpl(st, i), nrm, Q30_KNOWN, 2e-9,
+                              "amplitudes printed by the reference's apps/qsim_base.cc (AVX-512) for circuit_q30 -d 20 "
+                              "(BASELINE.md section 4); full-state comparison: tests/test_circuit_gpu.py") \
+            if os.path.basename(args.trace).startswith("q30_d20") else None
+        # second configuration BASELINE configs[1] names: the same circuit fused to 5 qubits (44 passes)
+        f5 = None
+        f5_trace = os.path.join(ROOT, "tests", "golden", "q30_d20_f5.trace")
+        if args.trace == TRACE and os.path.exists(f5_trace):
+            n5, ops5 = qsim_b200.read_trace(f5_trace)
+            t5 = []
+            for it in range(2 + args.steps):
+                ss.SetStateZero(st)
+                ss.DeviceSync()
+                sim.timer_start()
+                for op in ops5:
+                    sim.ApplyGate(op.qubits, op.matrix, st)
+                if it >= 2:
+                    t5.append(sim.timer_stop_ms())
+                else:
+                    sim.timer_stop_ms()
+            a5 = [ss.GetAmpl(st, i) for i in Q30_KNOWN]
+            f5 = {"workload": "circuit_q30 depth 20, max_fused_size 5: %d passes" % len(ops5), "ms_per_step": float(np.mean(t5)),
+                  "value": len(ops5) * pass_bytes / (float(np.mean(t5)) * 1e-3) / 1e9, "unit": "GB/s",
+                  "max_abs_err_vs_reference_amplitudes": float(max(abs(a - complex(*v)) for a, v in zip(a5, Q30_KNOWN.values())))}
+        del st
+        gpu_base = None
+        if not args.no_cpu_baseline and world == 1 and args.trace == TRACE:
+            gpu_base = gpu_reference_baseline(4)
+            if gpu_base.get("ms_per_circuit"):
+                gpu_base["ours_over_reference_cuda"] = gpu_base["ms_per_circuit"] / ms_per_step
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"circuits/circuit_q30 depth 20, {os.path.basename(args.trace)} "
-                                       f"(max_fused_size {os.path.basename(args.trace).split('_f')[-1].split('.')[0]}): {len(ops)} fused-gate passes on a "
-                                       f"2^{n}-amplitude fp32 state ({8 * amps / 2**30:.0f} GiB) per GPU; trace = reference parser+fuser output",
+                "config": {"workload": WORKLOAD if args.trace == TRACE else
+                           f"{os.path.basename(args.trace)}: {len(ops)} fused-gate passes on a 2^{n}-amplitude fp32 state",
                            "l2": "state (8 GiB) is 68x larger than L2: every pass streams from HBM",
                            "multi_gpu": "independent replicas" if world > 1 else "single GPU",
                            "wall_time_s_per_circuit": ms_per_step * 1e-3},
-                "roofline": roofline, "cpu_baseline": cpu,
+                "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "fused5": f5, "parity": parity,
                 "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_step, "amp0": [amp_out[0].real, amp_out[0].imag], "norm": nrm},
                 "gpu_launches": int(launches), "clocks": clocks,

@@ -117,6 +117,8 @@ int qb200_copy_h2d(qb200_ctx* ctx, int dtype, const void* host_src, void* dst, u
 int qb200_sync(qb200_ctx* ctx);
 /* The reference's static DeviceSync: cudaDeviceSynchronize on the current device. */
 int qb200_device_sync(void);
+/* cudaDeviceSynchronize on a given device (a multi-device state's DeviceSync loops over the devices). */
+int qb200_device_sync_on(int device);
 
 /* ---- Simulator (lib/simulator_cuda.h) ---------------------------------- */
 /* SimulatorCUDA::ApplyGate (:70-125): in place, num_targets in [0,6].

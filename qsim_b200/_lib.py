@@ -90,6 +90,7 @@ class SvStats(C.Structure):
 
 
 SIGNATURES.update({
+    "qb200_device_sync_on": (_i, [_i]),
     "qb200_state_alloc_on": (_i, [_vp, _u, _i, C.POINTER(_vp)]),
     "qb200_last_kernel_name": (C.c_char_p, [_vp]),
     "qb200_ctx_set_sm_limit": (_i, [_vp, _i]),

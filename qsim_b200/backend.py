@@ -103,6 +103,10 @@ class _Base:
     def launch_count(self) -> int:
         return int(self._lib.qb200_launch_count(self._ctx))
 
+    def last_kernel_name(self) -> str:
+        """the gate / expectation kernel the dispatcher chose for this object's last pass"""
+        return self._lib.qb200_last_kernel_name(self._ctx).decode()
+
     def set_tuning(self, key: str, value: int):
         self._check(self._lib.qb200_ctx_set_tuning(self._ctx, key.encode(), int(value)), "set_tuning")
 
@@ -128,7 +132,7 @@ class StateSpaceB200(_Base):
 
     def Create(self, num_qubits: int) -> State:
         p = C.c_void_p()
-        rc = self._lib.qb200_state_alloc(num_qubits, self._dt, C.byref(p))
+        rc = self._lib.qb200_state_alloc_on(self._ctx, num_qubits, self._dt, C.byref(p))  # on this object's device
         if rc == ERR_OOM:
             return self.Null()  # lib/vectorspace_cuda.h:90-95
         self._check(rc, "Create")

@@ -357,6 +357,21 @@ int qb200_device_sync(void) {
   return QB200_OK;
 }
 
+int qb200_device_sync_on(int device) {
+  int prev = 0;
+  if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return QB200_ERR_CUDA;
+  }
+  const cudaError_t e = cudaDeviceSynchronize();
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    (void) cudaGetLastError();
+    return QB200_ERR_CUDA;
+  }
+  return QB200_OK;
+}
+
 int qb200_reduce_batch_begin(qb200_ctx* ctx, uint32_t expected) {
   if (!ctx || ctx->batching) return QB200_ERR_INVALID;
   DeviceGuard guard(ctx);

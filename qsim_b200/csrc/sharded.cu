@@ -301,7 +301,7 @@ static int init_common(qb200_sv* sv, unsigned num_shards, unsigned num_qubits, i
   if ((1u << g) != num_shards || g > kMaxGlobal) return QB200_ERR_INVALID;
   if (dtype != QB200_F32 && dtype != QB200_F64) return QB200_ERR_INVALID;
   // same guard as lib/multiprocess_custatevecex.h:160-163: at least two local qubits
-  if (num_qubits < g + 2 || num_qubits > kMaxQubits) return QB200_ERR_INVALID;
+  if ((g > 0 && num_qubits < g + 2) || num_qubits > kMaxQubits) return QB200_ERR_INVALID;
   sv->n = num_qubits;
   sv->g = g;
   sv->nl = num_qubits - g;
@@ -533,14 +533,23 @@ static int timing_collect(qb200_sv* sv) {
 }
 
 // victims (logical, local) <-> incoming (logical, global); k <= g.
-static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* incoming, unsigned k) {
+static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* incoming_in, unsigned k) {
   if (k == 0) return QB200_OK;
   if (k > sv->g) return QB200_ERR_INVALID;
-  std::vector<unsigned> victims(victims_in, victims_in + k);
+  // victim j goes to the rank bit incoming j leaves: keep the caller's pairing, order the pairs by the victims'
+  // physical bits (the kernels want those ascending)
+  for (unsigned j = 0; j < k; ++j) {
+    if (victims_in[j] >= sv->n || incoming_in[j] >= sv->n) return QB200_ERR_INVALID;
+    if (sv->pos[victims_in[j]] >= sv->nl || sv->pos[incoming_in[j]] < sv->nl) return QB200_ERR_INVALID;
+  }
+  std::vector<unsigned> perm(k);
+  for (unsigned j = 0; j < k; ++j) perm[j] = j;
+  std::sort(perm.begin(), perm.end(), [&](unsigned a, unsigned b) { return sv->pos[victims_in[a]] < sv->pos[victims_in[b]]; });
+  std::vector<unsigned> victims(k), incoming(k);
   unsigned gb[kMaxGlobal];
   for (unsigned j = 0; j < k; ++j) {
-    if (victims[j] >= sv->n || incoming[j] >= sv->n) return QB200_ERR_INVALID;
-    if (sv->pos[victims[j]] >= sv->nl || sv->pos[incoming[j]] < sv->nl) return QB200_ERR_INVALID;
+    victims[j] = victims_in[perm[j]];
+    incoming[j] = incoming_in[perm[j]];
     gb[j] = sv->pos[incoming[j]] - sv->nl;
   }
   bool out_of_place = sv->swap_mode != 0;
@@ -551,8 +560,6 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
   const double sent = (double) shard_bytes(sv) * (1.0 - 1.0 / (double) (1u << k));
 
   if (out_of_place) {
-    // victims sorted by physical bit; victim j pairs with rank bit gb[j]
-    std::sort(victims.begin(), victims.end(), [&](unsigned a, unsigned b) { return sv->pos[a] < sv->pos[b]; });
     RemapGeom rg{};
     rg.k = k;
     rg.nl = sv->nl;
@@ -612,12 +619,12 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
         SV_TRY(local_bit_swap(sv, p, dst));
         *std::find(taken.begin(), taken.end(), p) = dst;
       }
-      // pair the victims (ascending physical bit) with the rank bits
+      // the lifting may have changed the order of the victims' bits: sort the pairs again
       std::vector<unsigned> ord(kk);
       for (unsigned j = 0; j < kk; ++j) ord[j] = off + j;
       std::sort(ord.begin(), ord.end(), [&](unsigned a, unsigned b) { return sv->pos[victims[a]] < sv->pos[victims[b]]; });
       unsigned lb[3], g3[3];
-      for (unsigned j = 0; j < kk; ++j) { lb[j] = sv->pos[victims[ord[j]]]; g3[j] = gb[off + j]; }
+      for (unsigned j = 0; j < kk; ++j) { lb[j] = sv->pos[victims[ord[j]]]; g3[j] = gb[ord[j]]; }
       timing_begin(sv);
       SV_TRY(barrier(sv));
       for (auto& s : sv->sh) {
@@ -631,7 +638,7 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
       timing_end(sv);
       for (unsigned j = 0; j < kk; ++j) {
         sv->pos[victims[ord[j]]] = sv->nl + g3[j];
-        sv->pos[incoming[off + j]] = lb[j];
+        sv->pos[incoming[ord[j]]] = lb[j];
       }
     }
   }

@@ -67,3 +67,31 @@ def test_circuit_q30_depth20_known_amplitudes(trace):
     # sampling at full size: sorted draws -> non-decreasing indices, all with non-zero probability
     samples = ss.Sample(st, 1000, 1)
     assert np.all(np.diff(samples.astype(np.int64)) >= 0)
+
+
+def test_circuit_q30_depth20_full_state_vs_reference_avx512():
+    """max |delta| and fidelity over the FULL 2^30 state against the reference's own
+    SimulatorAVX512 / AVX path (oracle/_ref, unmodified reference compiled in place, all host cores)."""
+    from oracle.oracle import SIMD_F32, RefEngine, ref_library_path
+    if not ref_library_path():
+        pytest.skip("oracle/_ref not built (reference tree was absent at build time)")
+    n, ops, ss, st = run_trace("q30_d20_f4.trace")
+    ref = RefEngine(SIMD_F32, n, os.cpu_count() or 1)
+    ref.set_zero()
+    for op in ops:
+        ref.apply_gate(op.qubits, op.matrix)
+    want = ref.to_numpy()
+    got = ss.to_numpy(st)
+    max_d, dot, nw, ng = 0.0, 0j, 0.0, 0.0
+    step = 1 << 26   # 0.5 GiB pieces keep the temporaries small
+    for lo in range(0, 1 << n, step):
+        a, b = want[lo:lo + step], got[lo:lo + step]
+        max_d = max(max_d, float(np.abs(a - b).max()))
+        a64, b64 = a.astype(np.complex128), b.astype(np.complex128)
+        dot += np.vdot(a64, b64)
+        nw += float(np.vdot(a64, a64).real)
+        ng += float(np.vdot(b64, b64).real)
+    fid = abs(dot) ** 2 / (nw * ng)
+    assert max_d <= 1e-5, max_d            # north_star: per-amplitude |delta| <= 1e-5
+    assert fid >= 1 - 1e-5, fid            # north_star: fidelity >= 1 - 1e-5
+    assert max_d <= 2e-7                   # what the kernels actually achieve (amplitudes are ~3e-5)
