@@ -258,15 +258,22 @@ def run_sharded(args, rank, world, local_rank, dist):
     # ---- end to end from host buffers (wall clock): plan (cached after the first call) + gates + 8 amplitudes + norm
     e2e_ms = []
     amps, nrm = None, None
+    phases = {"issue_ms": 0.0, "amplitudes_ms": 0.0, "norm_ms": 0.0}
     for it in range(1 + args.steps):
         barrier()
         t0 = time.perf_counter()
         one_run()
-        amps = [sv.GetAmpl(i) for i in range(8)]
+        t1 = time.perf_counter()
+        amps = [sv.GetAmpl(i) for i in range(8)]   # the first one waits for the circuit
+        t2 = time.perf_counter()
         nrm = sv.Norm()
         torch.cuda.synchronize()
+        t3 = time.perf_counter()
         if it >= 1:
-            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            e2e_ms.append((t3 - t0) * 1e3)
+            phases["issue_ms"] += (t1 - t0) * 1e3 / args.steps
+            phases["amplitudes_ms"] += (t2 - t1) * 1e3 / args.steps
+            phases["norm_ms"] += (t3 - t2) * 1e3 / args.steps
     t = torch.tensor([float(np.mean(e2e_ms))], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_step = float(t.item())
@@ -310,7 +317,8 @@ def run_sharded(args, rank, world, local_rank, dist):
                 "cpu_baseline": None,
                 "e2e": {"value": total_bytes / (e2e_step * 1e-3) / 1e9, "unit": "GB/s",
                         "h2d_bytes_per_step": sum(op.matrix.nbytes for op in ops), "d2h_bytes_per_step": 72,
-                        "ms_per_step": e2e_step, "amp0": [amps[0].real, amps[0].imag], "norm": nrm},
+                        "ms_per_step": e2e_step, "amp0": [amps[0].real, amps[0].imag], "norm": nrm,
+                        "host_phases_rank0": phases},
                 "gpu_launches": int(launches), "clocks": clocks}
         emit(line)
     sv.close()

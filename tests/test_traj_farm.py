@@ -87,3 +87,30 @@ def test_b200_trajectories_match_reference_cpu(circuit_file):
                                       extra_args=("-j", "3"))
         assert threaded["gate_passes"] == got["gate_passes"] and threaded["num"] == 16
         assert np.abs(np.array(threaded["sums"]) - np.array(got["sums"])).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_b200_trajectories_match_reference_cpu_at_26_qubits(tmp_path):
+    """BASELINE config 5's size (26 qubits, 512 MiB state, depolarizing noise) with a rotation circuit whose
+    single-qubit observables are O(0.1) -- on the RQC of the benchmark they are ~1e-10 and a wrong observable
+    would go unnoticed: three repetition ids on the B200 backend against the reference-CPU build of the same
+    driver (oracle/_ref/qsim_qtrajectory_ref, the reference's own CPU simulator) on the same seeds."""
+    if not (os.path.exists(REF) and os.path.exists(traj_farm.BINARY)):
+        pytest.skip("oracle/_ref or apps/_bin not built (the reference tree was absent at build time)")
+    p = tmp_path / "rot26"
+    p.write_text(rotation_circuit(26, 4, 11))
+    threads = ("-t", str(os.cpu_count() or 4))
+    ref = traj_farm.run_farm(str(p), 5, 3, gpus=1, p=0.02, max_fused_size=4, binary=REF, device_ids=[None],
+                             extra_args=threads)
+    got = traj_farm.run_farm(str(p), 5, 3, gpus=1, p=0.02, max_fused_size=4)
+    serial = traj_farm.run_farm(str(p), 5, 3, gpus=1, p=0.02, max_fused_size=4, extra_args=("-b", "0"))
+    assert got["n"] == 26 and got["gate_passes"] == ref["gate_passes"]
+    r, g, s = np.array(ref["sums"]), np.array(got["sums"]), np.array(serial["sums"])
+    assert np.abs(r / 3).max() > 0.1, "observables must not be trivially zero"
+    assert np.sum(np.abs(r / 3) > 0.05) >= 10
+    assert np.abs(s - r).max() < 3 * 2e-5, np.abs(s - r).max()   # the reference's expect.h loop on our kernels
+    assert np.abs(g - r).max() < 3 * 2e-5, np.abs(g - r).max()   # moments + batched Pauli strings
+    # the noise was sampled: at least one trajectory differs from the noiseless one
+    clean = traj_farm.run_farm(str(p), 5, 1, gpus=1, p=0.0, max_fused_size=4)
+    one = traj_farm.run_farm(str(p), 5, 3, gpus=1, p=0.02, max_fused_size=4)
+    assert np.abs(np.array(one["sums"]) / 3 - np.array(clean["sums"])).max() > 1e-3
