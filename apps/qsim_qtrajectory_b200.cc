@@ -10,7 +10,12 @@
 // Backend = include/qsim_b200/*.h (SimulatorB200 / StateSpaceB200), or -- when compiled with
 // -DQTRAJ_REFERENCE_CPU for the oracle build under oracle/_ref/ -- the reference's CPU
 // simulator selected by lib/simmux.h, so that the same seeds give the same Kraus choices and
-// the observable sums can be compared number by number.
+// the observable sums can be compared number by number; -DQTRAJ_REFERENCE_CUDA (nvcc) puts the
+// same driver on the reference's own CUDA backend (lib/simulator_cuda.h) = the GPU baseline.
+// B200 backend only: "-x 1" (default) shares the noiseless prefix of the fused gate list between
+// trajectories (include/qsim_b200/qtrajectory_b200.h), bit-identical sums, ~2.5x fewer gate passes at
+// p = 0.001; "-C amplitude_damp" replaces the depolarizing channel by amplitude damping with gamma = -p
+// (a non-unitary channel: Kraus operators sampled from expectation values, lib/qtrajectory.h:335-372).
 //
 // Role model: apps/qsim_qtrajectory_cuda.cu (amplitude/phase damping, X observables);
 // here: depolarizing noise after every gate qubit; observables = X_q and Z_q on every qubit
@@ -46,11 +51,16 @@
 #include "qtrajectory.h"
 #include "run_qsim.h"
 
-#ifdef QTRAJ_REFERENCE_CPU
+#if defined(QTRAJ_REFERENCE_CPU)
 #include "formux.h"
 #include "simmux.h"
+#elif defined(QTRAJ_REFERENCE_CUDA)
+#include "simulator_cuda.h"
+#define QTRAJ_REFERENCE_CPU  // same code path as the CPU checker: the reference's runner and expect.h
+#define QTRAJ_REFERENCE_IS_CUDA
 #else
 #include "qsim_b200/expect_b200.h"
+#include "qsim_b200/qtrajectory_b200.h"
 #include "qsim_b200/simulator_b200.h"
 #endif
 
@@ -69,12 +79,14 @@ struct Options {
   // contiguous sub-slices of the repetition ids: one worker's host phases (fusing, Kraus sampling, reading
   // results) overlap the other's kernels.  B200 backend only.
   unsigned workers = 1;
+  unsigned prefix = 1;            // 1: share the noiseless prefix between trajectories (B200 backend)
+  std::string channel = "depolarize";  // or "amplitude_damp" (gamma = p)
 };
 
 Options Parse(int argc, char* argv[]) {
   Options o;
   int k;
-  while ((k = getopt(argc, argv, "c:d:p:0:n:f:t:v:b:j:")) != -1) {
+  while ((k = getopt(argc, argv, "c:d:p:0:n:f:t:v:b:j:x:C:")) != -1) {
     switch (k) {
       case 'c': o.circuit_file = optarg; break;
       case 'd': o.maxtime = std::atoi(optarg); break;
@@ -86,9 +98,12 @@ Options Parse(int argc, char* argv[]) {
       case 'v': o.verbosity = std::atoi(optarg); break;
       case 'b': o.batch = std::atoi(optarg); break;
       case 'j': o.workers = std::max(1, std::atoi(optarg)); break;
+      case 'x': o.prefix = std::atoi(optarg); break;
+      case 'C': o.channel = optarg; break;
       default:
         std::fprintf(stderr, "usage: %s -c circuit [-d maxtime] [-p prob] [-0 traj0] [-n num] "
-                             "[-f max_fused_size] [-t threads] [-v verbosity] [-b batch] [-j workers]\n", argv[0]);
+                             "[-f max_fused_size] [-t threads] [-v verbosity] [-b batch] [-j workers] [-x prefix_sharing] "
+                             "[-C depolarize|amplitude_damp]\n", argv[0]);
         std::exit(1);
     }
   }
@@ -162,7 +177,16 @@ int main(int argc, char* argv[]) {
   using fp_type = float;
   const Options opt = Parse(argc, argv);
 
-#ifdef QTRAJ_REFERENCE_CPU
+#if defined(QTRAJ_REFERENCE_IS_CUDA)
+  struct Factory {
+    using Simulator = Counting<qsim::SimulatorCUDA<fp_type>>;
+    using StateSpace = Simulator::StateSpace;
+    explicit Factory(unsigned) {}
+    StateSpace CreateStateSpace() const { return StateSpace(StateSpace::Parameter{}); }
+    Simulator CreateSimulator() const { return Simulator(); }
+  };
+  Factory factory(0);
+#elif defined(QTRAJ_REFERENCE_CPU)
   struct Factory {
     using Simulator = Counting<qsim::Simulator<For>>;
     using StateSpace = Simulator::StateSpace;
@@ -185,7 +209,11 @@ int main(int argc, char* argv[]) {
   using Simulator = Factory::Simulator;
   using StateSpace = Factory::StateSpace;
   using Fuser = MultiQubitGateFuser<IO>;
+#ifdef QTRAJ_REFERENCE_CPU
   using Runner = QSimRunner<IO, Fuser, Factory>;
+#else
+  using Runner = PrefixSharingRunner<IO, Fuser, Factory>;  // QSimRunner's flow unless a cache is armed
+#endif
   using QTSimulator = QuantumTrajectorySimulator<IO, Runner>;
 
   Circuit<Operation<fp_type>> circuit;
@@ -194,7 +222,12 @@ int main(int argc, char* argv[]) {
     std::fprintf(stderr, "cannot read circuit\n");
     return 1;
   }
-  const auto ncircuit = MakeNoisy(circuit, Cirq::DepolarizingChannel<fp_type>(opt.p));
+  if (opt.channel != "depolarize" && opt.channel != "amplitude_damp") {
+    std::fprintf(stderr, "unknown channel %s\n", opt.channel.c_str());
+    return 1;
+  }
+  const auto ncircuit = opt.channel == "depolarize" ? MakeNoisy(circuit, Cirq::DepolarizingChannel<fp_type>(opt.p))
+                                                    : MakeNoisy(circuit, Cirq::AmplitudeDampingChannel<fp_type>(opt.p));
   const auto observables = Observables<fp_type>(circuit.num_qubits);
 #ifndef QTRAJ_REFERENCE_CPU
   // the observables are the same for every trajectory: reduce their strings to (qubits, matrix) once
@@ -216,6 +249,7 @@ int main(int argc, char* argv[]) {
   PassCount passes;
   Clock::time_point first_start = Clock::time_point::max(), last_end = Clock::time_point::min();
   std::mutex merge;
+  uint64_t prefix_skipped = 0, prefix_clean = 0;  // fused gates not applied thanks to the shared prefix; noiseless trajectories
   std::atomic<unsigned> ready{0};
   std::atomic<bool> failed{false};
 
@@ -236,6 +270,19 @@ int main(int argc, char* argv[]) {
     if (!ok) std::fprintf(stderr, "not enough memory\n");
     typename QTSimulator::Stat stat;
     std::vector<std::complex<double>> local(observables.size(), 0.0);
+#ifndef QTRAJ_REFERENCE_CPU
+    // noiseless prefix shared between this worker's trajectories (only the unitary-mixture channel defers the
+    // whole circuit into one flush; amplitude damping flushes at every channel and gains nothing)
+    typename Runner::Cache cache;
+    const bool share = opt.prefix != 0 && opt.channel == "depolarize" && ok;
+    std::vector<std::complex<double>> clean_evals;
+    if (share) {
+      std::vector<std::variant<const Gate<fp_type>*, const Operation<fp_type>*>> clean_ops;
+      for (const auto& op : ncircuit.ops)
+        if (!OpGetAlternative<Channel<fp_type>>(op)) clean_ops.push_back(&op);
+      ok = cache.template Build<Fuser>(param, circuit.num_qubits, clean_ops, state_space, simulator);
+    }
+#endif
     if (ok) {
       // one untimed trajectory: context creation, kernel loading, scratch growth
       state_space.SetStateZero(state);
@@ -249,6 +296,9 @@ int main(int argc, char* argv[]) {
     const auto t0 = Clock::now();
     for (unsigned i = 0; i < count && !failed.load(); ++i) {
       state_space.SetStateZero(state);
+#ifndef QTRAJ_REFERENCE_CPU
+      if (share) Runner::Arm(&cache);
+#endif
       // seed = repetition id, as QuantumTrajectorySimulator::RunBatch does (lib/qtrajectory.h:268)
       if (!QTSimulator::RunOnce(param, ncircuit, uint64_t{first} + i, state_space, simulator, state, stat)) {
         failed = true;
@@ -256,7 +306,14 @@ int main(int argc, char* argv[]) {
       }
 #ifndef QTRAJ_REFERENCE_CPU
       if (opt.batch) {
+        // a trajectory without any noise event ends in the noiseless state: its observables are computed once
+        const bool clean = share && Runner::was_clean();
+        if (clean && !clean_evals.empty()) {
+          for (std::size_t k = 0; k < observables.size(); ++k) local[k] += clean_evals[k];
+          continue;
+        }
         const auto evals = ExpectationValues(plan, simulator, state, opt.batch >= 2);
+        if (clean) clean_evals = evals;
         for (std::size_t k = 0; k < observables.size(); ++k) local[k] += evals[k];
         continue;
       }
@@ -267,6 +324,10 @@ int main(int argc, char* argv[]) {
     }
     const auto t1 = Clock::now();
     std::lock_guard<std::mutex> lock(merge);
+#ifndef QTRAJ_REFERENCE_CPU
+    prefix_skipped += cache.gates_skipped;
+    prefix_clean += cache.clean_runs;
+#endif
     for (std::size_t k = 0; k < sums.size(); ++k) sums[k] += local[k];
     passes.gates += g_passes.gates;
     passes.expects += g_passes.expects;
@@ -287,10 +348,12 @@ int main(int argc, char* argv[]) {
 
   std::printf("{\"n\": %u, \"traj0\": %u, \"num\": %u, \"num_ops\": %zu, \"num_observables\": %zu, "
               "\"gate_passes\": %llu, \"expect_passes\": %llu, \"moment_calls\": %llu, \"workers\": %u, "
+              "\"prefix_gates_skipped\": %llu, \"noiseless_trajectories\": %llu, \"channel\": \"%s\", "
               "\"seconds\": %.6f, \"sums\": [",
               circuit.num_qubits, opt.traj0, opt.num, ncircuit.ops.size(), observables.size(),
               (unsigned long long) passes.gates, (unsigned long long) passes.expects,
-              (unsigned long long) passes.moment_calls, workers, seconds);
+              (unsigned long long) passes.moment_calls, workers, (unsigned long long) prefix_skipped,
+              (unsigned long long) prefix_clean, opt.channel.c_str(), seconds);
   for (std::size_t k = 0; k < sums.size(); ++k) {
     std::printf("%s%.9g, %.9g", k ? ", " : "", sums[k].real(), sums[k].imag());
   }

@@ -111,6 +111,8 @@ int qb200_state_free(void* state);
 /* Copy state->state / state->host / host->state (:112-160).  `count` is in
  * scalars; host buffers may be pageable.  Blocking, like the reference. */
 int qb200_copy_d2d(qb200_ctx* ctx, int dtype, const void* src, void* dst, uint64_t count);
+/* the same device-to-device copy enqueued on the context's stream without waiting for it */
+int qb200_copy_d2d_async(qb200_ctx* ctx, int dtype, const void* src, void* dst, uint64_t count);
 int qb200_copy_d2h(qb200_ctx* ctx, int dtype, const void* src, void* host_dst, uint64_t count);
 int qb200_copy_h2d(qb200_ctx* ctx, int dtype, const void* host_src, void* dst, uint64_t count);
 /* VectorSpaceCUDA::DeviceSync (:162-164): waits for the context's stream. */

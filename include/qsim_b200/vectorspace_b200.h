@@ -134,6 +134,15 @@ class VectorSpaceB200 {
     return true;
   }
 
+  // Not in the reference: the same copy enqueued on this object's stream, the host does not wait
+  // (qtrajectory_b200.h restores checkpoints with it).
+  bool CopyAsync(const Vector& src, Vector& dest) const {
+    if (src.num_qubits() != dest.num_qubits()) return false;
+    QB200_CHECK(ctx(), qb200_copy_d2d_async(ctx(), b200::DType<FP>::value, src.get(), dest.get(),
+                                            Impl::MinSize(src.num_qubits())));
+    return true;
+  }
+
   bool Copy(const Vector& src, fp_type* dest) const {
     QB200_CHECK(ctx(), qb200_copy_d2h(ctx(), b200::DType<FP>::value, src.get(), dest,
                                       Impl::MinSize(src.num_qubits())));

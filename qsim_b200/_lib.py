@@ -34,6 +34,7 @@ SIGNATURES = {
     "qb200_state_alloc": (_i, [_u, _i, C.POINTER(_vp)]),
     "qb200_state_free": (_i, [_vp]),
     "qb200_copy_d2d": (_i, [_vp, _i, _vp, _vp, _u64]),
+    "qb200_copy_d2d_async": (_i, [_vp, _i, _vp, _vp, _u64]),
     "qb200_copy_d2h": (_i, [_vp, _i, _vp, _vp, _u64]),
     "qb200_copy_h2d": (_i, [_vp, _i, _vp, _vp, _u64]),
     "qb200_sync": (_i, [_vp]),

@@ -333,6 +333,13 @@ int qb200_copy_d2d(qb200_ctx* ctx, int dtype, const void* src, void* dst, uint64
   return QB200_OK;
 }
 
+int qb200_copy_d2d_async(qb200_ctx* ctx, int dtype, const void* src, void* dst, uint64_t count) {
+  if (!ctx || !src || !dst) return QB200_ERR_INVALID;
+  DeviceGuard guard(ctx);
+  QB_CUDA(ctx, cudaMemcpyAsync(dst, src, count * scalar_bytes(dtype), cudaMemcpyDeviceToDevice, ctx->stream));
+  return QB200_OK;
+}
+
 int qb200_copy_d2h(qb200_ctx* ctx, int dtype, const void* src, void* host_dst, uint64_t count) {
   if (!ctx || !src || !host_dst) return QB200_ERR_INVALID;
   DeviceGuard guard(ctx);

@@ -68,16 +68,22 @@ def test_b200_trajectories_match_reference_cpu(circuit_file):
         # default (-b 2): single-qubit observables from the reduced density matrices (csrc/moments.cu), the
         # Pauli strings batched -- fewer passes, same sums to fp32 round-off
         got = traj_farm.run_farm(circuit_file, 0, 16, gpus=1, p=0.05, max_fused_size=fused)
-        assert got["gate_passes"] == ref["gate_passes"] and got["expect_passes"] < ref["expect_passes"]
+        # ... and the noiseless prefix of the fused gate list is shared between trajectories (-x 1, default):
+        # fewer gate passes, bit-identical sums
+        assert got["gate_passes"] + got["prefix_gates_skipped"] == ref["gate_passes"]
+        assert got["expect_passes"] < ref["expect_passes"]
+        plain = traj_farm.run_farm(circuit_file, 0, 16, gpus=1, p=0.05, max_fused_size=fused, extra_args=("-x", "0"))
+        assert plain["gate_passes"] == ref["gate_passes"] and plain["prefix_gates_skipped"] == 0
+        assert plain["sums"] == got["sums"]
         err = np.abs(np.array(got["sums"]) - np.array(ref["sums"])).max()
         assert err < 16 * 2e-5, err
         assert np.abs(np.array(ref["mean"])).max() > 0.1
         # "-b 1" = every operator string through its own pass, all enqueued and read after one synchronisation;
         # "-b 0" = the reference's lib/expect.h, one synchronisation per string: same kernels, identical sums
         batched = traj_farm.run_farm(circuit_file, 0, 16, gpus=1, p=0.05, max_fused_size=fused,
-                                     extra_args=("-b", "1"))
+                                     extra_args=("-b", "1", "-x", "0"))
         serial = traj_farm.run_farm(circuit_file, 0, 16, gpus=1, p=0.05, max_fused_size=fused,
-                                    extra_args=("-b", "0"))
+                                    extra_args=("-b", "0", "-x", "0"))
         assert serial["sums"] == batched["sums"]
         assert serial["expect_passes"] == batched["expect_passes"] == ref["expect_passes"]
         assert np.abs(np.array(got["sums"]) - np.array(serial["sums"])).max() < 16 * 2e-5
@@ -85,7 +91,7 @@ def test_b200_trajectories_match_reference_cpu(circuit_file):
         # same trajectories, sums added in a different order
         threaded = traj_farm.run_farm(circuit_file, 0, 16, gpus=1, p=0.05, max_fused_size=fused,
                                       extra_args=("-j", "3"))
-        assert threaded["gate_passes"] == got["gate_passes"] and threaded["num"] == 16
+        assert threaded["gate_passes"] + threaded["prefix_gates_skipped"] == ref["gate_passes"] and threaded["num"] == 16
         assert np.abs(np.array(threaded["sums"]) - np.array(got["sums"])).max() < 1e-9
 
 
@@ -104,7 +110,7 @@ def test_b200_trajectories_match_reference_cpu_at_26_qubits(tmp_path):
                              extra_args=threads)
     got = traj_farm.run_farm(str(p), 5, 3, gpus=1, p=0.02, max_fused_size=4)
     serial = traj_farm.run_farm(str(p), 5, 3, gpus=1, p=0.02, max_fused_size=4, extra_args=("-b", "0"))
-    assert got["n"] == 26 and got["gate_passes"] == ref["gate_passes"]
+    assert got["n"] == 26 and got["gate_passes"] + got["prefix_gates_skipped"] == ref["gate_passes"]
     r, g, s = np.array(ref["sums"]), np.array(got["sums"]), np.array(serial["sums"])
     assert np.abs(r / 3).max() > 0.1, "observables must not be trivially zero"
     assert np.sum(np.abs(r / 3) > 0.05) >= 10
@@ -114,3 +120,34 @@ def test_b200_trajectories_match_reference_cpu_at_26_qubits(tmp_path):
     clean = traj_farm.run_farm(str(p), 5, 1, gpus=1, p=0.0, max_fused_size=4)
     one = traj_farm.run_farm(str(p), 5, 3, gpus=1, p=0.02, max_fused_size=4)
     assert np.abs(np.array(one["sums"]) / 3 - np.array(clean["sums"])).max() > 1e-3
+
+
+@pytest.mark.gpu
+def test_weak_noise_shares_most_of_the_circuit(circuit_file):
+    """p = 0.001 (the benchmark's noise level): most trajectories are noiseless, the others start from a deep
+    checkpoint; sums bit-identical to the plain runner and equal to the reference CPU run."""
+    if not (os.path.exists(REF) and os.path.exists(traj_farm.BINARY)):
+        pytest.skip("oracle/_ref or apps/_bin not built")
+    ref = traj_farm.run_farm(circuit_file, 0, 64, gpus=1, p=0.001, binary=REF, device_ids=[None])
+    got = traj_farm.run_farm(circuit_file, 0, 64, gpus=1, p=0.001)
+    plain = traj_farm.run_farm(circuit_file, 0, 64, gpus=1, p=0.001, extra_args=("-x", "0"))
+    assert got["sums"] == plain["sums"]
+    assert np.abs(np.array(got["sums"]) - np.array(ref["sums"])).max() < 64 * 2e-5
+    assert got["noiseless_trajectories"] >= 32 and got["gate_passes"] < 0.4 * plain["gate_passes"]
+
+
+@pytest.mark.gpu
+def test_amplitude_damping_trajectories_match_reference_cpu(circuit_file):
+    """a NON-unitary channel (lib/channels_cirq.h:274-311): every channel flushes the deferred gates and samples
+    its Kraus operator from expectation values of K^dagger K on the current state, then renormalises
+    (lib/qtrajectory.h:335-372) -- the ExpectationValue / Norm / Multiply path of the backend inside the
+    trajectory loop.  Same repetition ids as the reference CPU simulator => same choices => same sums."""
+    if not (os.path.exists(REF) and os.path.exists(traj_farm.BINARY)):
+        pytest.skip("oracle/_ref or apps/_bin not built")
+    args = ("-C", "amplitude_damp")
+    ref = traj_farm.run_farm(circuit_file, 0, 6, gpus=1, p=0.05, binary=REF, device_ids=[None], extra_args=args)
+    got = traj_farm.run_farm(circuit_file, 0, 6, gpus=1, p=0.05, extra_args=args)
+    assert got["gate_passes"] == ref["gate_passes"]
+    assert np.abs(np.array(got["sums"]) - np.array(ref["sums"])).max() < 6 * 5e-5
+    clean = traj_farm.run_farm(circuit_file, 0, 1, gpus=1, p=0.0, binary=REF, device_ids=[None])
+    assert np.abs(np.array(ref["sums"]) / 6 - np.array(clean["sums"])).max() > 1e-3   # the damping matters
