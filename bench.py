@@ -210,7 +210,8 @@ def run_sharded(args, rank, world, local_rank, dist):
     trace = os.path.join(ROOT, "tests", "golden", f"rqc_q{n}_d20_f4.trace")
     nq, ops = qsim_b200.read_trace(trace)
     assert nq == n
-    sv = ShardedStateB200.multi_process(dist, n, local_rank)
+    host_group = dist.new_group(backend="gloo")   # host-side collectives of qb200_comm: a few doubles, CPU tensors
+    sv = ShardedStateB200.multi_process(dist, n, local_rank, host_group=host_group)
     for kv in args.tune:
         key, val = kv.split("=")
         sv.set_option(key, int(val))
@@ -264,7 +265,7 @@ def run_sharded(args, rank, world, local_rank, dist):
         t0 = time.perf_counter()
         one_run()
         t1 = time.perf_counter()
-        amps = [sv.GetAmpl(i) for i in range(8)]   # the first one waits for the circuit
+        amps = sv.GetAmpls(range(8))   # waits for the circuit; one host-side collective
         t2 = time.perf_counter()
         nrm = sv.Norm()
         torch.cuda.synchronize()
@@ -288,7 +289,8 @@ def run_sharded(args, rank, world, local_rank, dist):
             gold = json.load(f).get(f"rqc_q{n}_d20_f4")
         if gold and args.shard_qubits == 30:
             known = {int(i): tuple(a) for i, a in zip(gold["indices"], gold["amplitudes"])}
-            parity = parity_block(sv.GetAmpl, nrm, known, 5e-8,
+            vals = dict(zip(known, sv.GetAmpls(list(known))))
+            parity = parity_block(vals.get, nrm, known, 5e-8,
                                   "tests/golden/rqc_amplitudes.json: the same circuit on ONE GPU through the single-GPU path "
                                   "(q31 also equal to the reference AVX-512 simulator to 1e-10)")
             parity["golden_norm"] = gold["norm"]
@@ -314,6 +316,7 @@ def run_sharded(args, rank, world, local_rank, dist):
                              "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})"},
                 "swap": {"swaps_per_circuit": swaps, "bytes_sent_per_rank_per_circuit": sent,
                          "exchange_ms_per_circuit": exch_ms / args.steps,
+                         "barrier_wait_ms_per_circuit_rank0": stats["barrier_wait_ms"] / args.steps,
                          "nvlink_GBps_per_direction": sent / (exch_ms / args.steps * 1e-3) / 1e9 if exch_ms > 0 else None,
                          "nvlink_peak_GBps_per_direction": 900.0},
                 "parity": parity,

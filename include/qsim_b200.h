@@ -279,7 +279,8 @@ typedef struct {
   uint64_t local_swap_passes;    /* 2-qubit SWAP passes (in-place exchange of low bits, canonicalisation) */
   uint64_t gate_passes;
   double bytes_sent_per_shard;   /* sum over exchanges of shard_bytes * (1 - 2^-k) */
-  double exchange_ms;            /* device time of the exchanges (CUDA events on the first local shard) */
+  double exchange_ms;            /* device time of the exchange kernels (CUDA events on the first local shard) */
+  double barrier_wait_ms;        /* device time that shard spent in the barriers around them (skew between GPUs) */
 } qb200_sv_stats;
 
 int qb200_sv_create(const int* devices, unsigned num_shards, unsigned num_qubits, int dtype, qb200_sv** sv);
@@ -309,6 +310,8 @@ int qb200_sv_set_state_zero(qb200_sv* sv);
 int qb200_sv_set_state_uniform(qb200_sv* sv);
 int qb200_sv_reset_map(qb200_sv* sv);  /* identity map without moving data: only before (re)initialising the state */
 int qb200_sv_get_ampl(qb200_sv* sv, uint64_t i, double out_re_im[2]);
+/* several amplitudes with ONE host-side collective (multi-process states): out[2j], out[2j+1] = amplitude indices[j] */
+int qb200_sv_get_ampls(qb200_sv* sv, const uint64_t* indices, uint64_t count, double* out_re_im);
 int qb200_sv_set_ampl(qb200_sv* sv, uint64_t i, double re, double im);
 int qb200_sv_bulk_set_ampl(qb200_sv* sv, uint64_t mask, uint64_t bits, double re, double im, int exclude);
 int qb200_sv_norm(qb200_sv* sv, double* out);

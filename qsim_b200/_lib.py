@@ -87,7 +87,7 @@ class Gate(C.Structure):
 class SvStats(C.Structure):
     """qb200_sv_stats"""
     _fields_ = [("swaps", _u64), ("local_swap_passes", _u64), ("gate_passes", _u64),
-                ("bytes_sent_per_shard", _d), ("exchange_ms", _d)]
+                ("bytes_sent_per_shard", _d), ("exchange_ms", _d), ("barrier_wait_ms", _d)]
 
 
 SIGNATURES.update({
@@ -117,6 +117,7 @@ SIGNATURES.update({
     "qb200_sv_set_state_uniform": (_i, [_vp]),
     "qb200_sv_reset_map": (_i, [_vp]),
     "qb200_sv_get_ampl": (_i, [_vp, _u64, _pd]),
+    "qb200_sv_get_ampls": (_i, [_vp, _pu64, _u64, _pd]),
     "qb200_sv_set_ampl": (_i, [_vp, _u64, _d, _d]),
     "qb200_sv_bulk_set_ampl": (_i, [_vp, _u64, _u64, _d, _d, _i]),
     "qb200_sv_norm": (_i, [_vp, _pd]),

@@ -15,6 +15,7 @@
 // allgather / allreduce / barrier callbacks, the analogue of custatevecExCommunicator,
 // lib/multiprocess_custatevecex.h:82-87).
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -36,45 +37,77 @@ constexpr unsigned kMinInplaceBit = 4;    // in-place exchange: victims below th
 // exchange kernel, out of place: every amplitude of the local shard goes to its place in the NEW layout, which
 // is a buffer of this or of a peer GPU.  The k victim bits of the local index select the destination shard; the
 // remaining local bits are packed (order kept) into the low n_local - k bits of the new local index and this
-// shard's own value of the k exchanged rank bits becomes the top k bits.  Reads are local and contiguous; a
-// warp's 16-byte stores fall into runs of 2^lbits[0] amplitudes per destination, and because the packed index
-// keeps those runs adjacent, a warp writes whole 128-byte lines whatever the victim bits are -- no local SWAP
-// passes in front of the exchange.  Push only: nothing is read over NVLink.
+// shard's own value of the k exchanged rank bits becomes the top k bits.  Push only: nothing is read over NVLink.
+//
+// A CTA moves tiles of 2^T consecutive source amplitudes (16 KB) through shared memory: coalesced 16-byte loads,
+// a scatter inside shared memory that sorts the tile by the victim bits it contains, then coalesced 16-byte
+// stores -- every destination receives runs of >= 2 KB whatever the victim bits are (victims on bits 0..2 would
+// otherwise reach the link as 8..64-byte pieces: 200-400 GB/s instead of 690), so no local SWAP pass is needed in
+// front of the exchange.  Victim bits above the tile pick the destination per tile; tiles are walked with those
+// bits fastest and XOR-ed with this shard's own value, so at any moment the shards of a group send to DIFFERENT
+// destinations (walking a shard in address order makes all of them hit the same destination at once: 290 GB/s).
 // ---------------------------------------------------------------------------------------------------------
+constexpr unsigned kTileBits = 11;  // 2^11 amplitudes per tile
+constexpr int kRemapThreads = 256;
+
 struct RemapGeom {
   void* dst[kMaxShards];   // new buffer of the shard whose exchanged rank bits equal v
-  uint64_t items;          // vector items in the shard
-  uint32_t k, my, vshift, nl;
-  uint32_t lbits[kMaxGlobal];  // ascending
+  uint64_t tiles;          // 2^(nl - T)
+  uint32_t k, kl, my, nl, T;
+  uint32_t lbits[kMaxGlobal];  // ascending; the first kl are below T
 };
 
-template <typename V>
-__global__ void __launch_bounds__(256)
-k_remap_push(const V* __restrict__ src, const __grid_constant__ RemapGeom g) {
-  constexpr int U = 4;
-  const uint64_t stride = uint64_t{gridDim.x} * blockDim.x;
-  for (uint64_t t0 = blockIdx.x * uint64_t{blockDim.x} + threadIdx.x; t0 < g.items; t0 += stride * U) {
-    V x[U];
-    uint64_t t[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      t[u] = t0 + u * stride;
-      if (t[u] < g.items) x[u] = src[t[u]];
+// FP = float: 16-byte items hold two amplitudes; FP = double: one.
+template <typename FP>
+__global__ void __launch_bounds__(kRemapThreads)
+k_remap_push(const FP* __restrict__ src, const __grid_constant__ RemapGeom g) {
+  using A = typename Vec2<FP>::type;          // one amplitude
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  A* tile = reinterpret_cast<A*>(smem_raw);
+  constexpr int APT = sizeof(FP) == 4 ? 2 : 1;               // amplitudes per 16-byte item
+  const uint32_t tile_amps = 1u << g.T;
+  const uint32_t items = tile_amps / APT;                    // 16-byte items per tile
+  const uint32_t kh = g.k - g.kl;
+  const uint32_t sub_bits = g.T - g.kl;                      // log2(amplitudes per destination run)
+  const uint32_t my_high = g.my >> g.kl;
+  for (uint64_t c = blockIdx.x; c < g.tiles; c += gridDim.x) {
+    // tile counter -> tile index: the kh victim bits above the tile vary fastest, XOR-ed with this shard's value
+    const uint32_t v_high = ((uint32_t) c & ((1u << kh) - 1)) ^ my_high;
+    uint64_t tau = c >> kh;                                  // bits of the tile index outside the victims
+    for (uint32_t j = g.kl; j < g.k; ++j) {                  // insert the victim bits, lowest first
+      const uint32_t b = g.lbits[j] - g.T;
+      const uint64_t lo = tau & ((uint64_t{1} << b) - 1);
+      tau = (((tau >> b) << 1 | ((v_high >> (j - g.kl)) & 1)) << b) | lo;
     }
+    const uint64_t packed_high = c >> kh;                    // the same bits with the victims squeezed out
+    // ---- load (coalesced) and scatter into shared memory, sorted by the low victim bits
+    const uint4* in = reinterpret_cast<const uint4*>(src) + tau * items;
+    __syncthreads();                                         // the previous tile has been read out
+    for (uint32_t it = threadIdx.x; it < items; it += kRemapThreads) {
+      const uint4 x = in[it];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (t[u] >= g.items) continue;
-      uint64_t idx = t[u] << g.vshift;   // amplitude index of the item's first amplitude
-      uint32_t v = 0;
-      // remove the victim bits, highest first, collecting their values
-      for (int j = (int) g.k - 1; j >= 0; --j) {
-        const uint32_t b = g.lbits[j];
-        v |= (uint32_t) ((idx >> b) & 1) << j;
-        const uint64_t lo = idx & ((uint64_t{1} << b) - 1);
-        idx = ((idx >> (b + 1)) << b) | lo;
+      for (int a = 0; a < APT; ++a) {
+        uint32_t i = it * APT + a, v = 0, r = i;
+        for (int j = (int) g.kl - 1; j >= 0; --j) {
+          const uint32_t b = g.lbits[j];
+          v |= ((r >> b) & 1u) << j;
+          r = ((r >> (b + 1)) << b) | (r & ((1u << b) - 1));
+        }
+        const uint32_t p = (v << sub_bits) | r;
+        if constexpr (APT == 2) {
+          reinterpret_cast<uint2*>(tile)[p] = a == 0 ? make_uint2(x.x, x.y) : make_uint2(x.z, x.w);
+        } else {
+          reinterpret_cast<uint4*>(tile)[p] = x;
+        }
       }
-      idx |= uint64_t{g.my} << (g.nl - g.k);
-      reinterpret_cast<V*>(g.dst[v])[idx >> g.vshift] = x[u];
+    }
+    __syncthreads();
+    // ---- read out linearly: run v_low of the tile goes, contiguously, to destination v_low | v_high << kl
+    for (uint32_t it = threadIdx.x; it < items; it += kRemapThreads) {
+      const uint32_t p = it * APT;
+      const uint32_t v = (p >> sub_bits) | (v_high << g.kl);
+      const uint64_t d = (uint64_t{g.my} << (g.nl - g.k)) | (packed_high << sub_bits) | (p & ((1u << sub_bits) - 1));
+      reinterpret_cast<uint4*>(g.dst[v])[d / APT] = reinterpret_cast<const uint4*>(tile)[it];
     }
   }
 }
@@ -137,7 +170,8 @@ struct Shard {
 struct SvStats {
   uint64_t swaps = 0, local_passes = 0, gate_passes = 0;
   double bytes_sent_per_shard = 0;   // summed over swaps
-  double exchange_ms = 0;            // device time (events on the first local shard's stream)
+  double exchange_ms = 0;            // device time of the exchange kernels (events on the first local shard's stream)
+  double wait_ms = 0;                // device time the first local shard spent in the barriers around them (rank skew)
 };
 
 }  // namespace qb200
@@ -168,7 +202,7 @@ struct qb200_sv {
   SvStats stats;
   std::vector<uint64_t> plan_key;        // gate structure + global set the cached schedule was made for
   std::vector<int64_t> plan_steps;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;  // exchange timing, first local shard
+  std::vector<std::array<cudaEvent_t, 4>> ev_quads;  // exchange timing, first local shard (timing_mark)
   size_t ev_used = 0;
   int last_error = 0;
 };
@@ -505,28 +539,30 @@ static unsigned pick_bits(unsigned rank, const unsigned* gb, unsigned k) {
   return v;
 }
 
-static void timing_begin(qb200_sv* sv) {
-  if (sv->ev_used == sv->ev_pairs.size()) {
-    DevScope d(sv->sh[0].device);
-    cudaEvent_t a = nullptr, b = nullptr;
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
-    sv->ev_pairs.emplace_back(a, b);
+// Four events per exchange on the first local shard's stream: [0] before the leading barrier, [1] kernel start,
+// [2] kernel end, [3] after the trailing barrier.  exchange_ms = [1]..[2]; wait_ms = the two barrier stretches.
+static void timing_mark(qb200_sv* sv, int which) {
+  DevScope d(sv->sh[0].device);
+  if (which == 0 && sv->ev_used == sv->ev_quads.size()) {
+    std::array<cudaEvent_t, 4> q{};
+    for (auto& e : q) cudaEventCreate(&e);
+    sv->ev_quads.push_back(q);
   }
-  DevScope d(sv->sh[0].device);
-  cudaEventRecord(sv->ev_pairs[sv->ev_used].first, sv->sh[0].stream);
-}
-static void timing_end(qb200_sv* sv) {
-  DevScope d(sv->sh[0].device);
-  cudaEventRecord(sv->ev_pairs[sv->ev_used].second, sv->sh[0].stream);
-  ++sv->ev_used;
+  cudaEventRecord(sv->ev_quads[sv->ev_used][which], sv->sh[0].stream);
+  if (which == 3) ++sv->ev_used;
 }
 static int timing_collect(qb200_sv* sv) {
   SV_TRY(sync_all(sv));
   for (size_t i = 0; i < sv->ev_used; ++i) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, sv->ev_pairs[i].first, sv->ev_pairs[i].second) == cudaSuccess) sv->stats.exchange_ms += ms;
-    else (void) cudaGetLastError();
+    const auto& q = sv->ev_quads[i];
+    float pre = 0, run = 0, post = 0;
+    if (cudaEventElapsedTime(&pre, q[0], q[1]) == cudaSuccess && cudaEventElapsedTime(&run, q[1], q[2]) == cudaSuccess &&
+        cudaEventElapsedTime(&post, q[2], q[3]) == cudaSuccess) {
+      sv->stats.exchange_ms += run;
+      sv->stats.wait_ms += pre + post;
+    } else {
+      (void) cudaGetLastError();
+    }
   }
   sv->ev_used = 0;
   return QB200_OK;
@@ -553,6 +589,17 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
     gb[j] = sv->pos[incoming[j]] - sv->nl;
   }
   bool out_of_place = sv->swap_mode != 0;
+  {
+    // the push kernel sorts tiles of 2^T amplitudes by the victim bits they contain: every destination run must
+    // hold at least one 16-byte item (a shard of a handful of qubits with all of them victims does not qualify)
+    const unsigned T = std::min<unsigned>(kTileBits, sv->nl);
+    unsigned kl = 0;
+    for (unsigned j = 0; j < k; ++j) kl += sv->pos[victims[j]] < T;
+    if (T < kl + (sv->dtype == QB200_F32 ? 1u : 0u)) {
+      if (sv->swap_mode == 1) return QB200_ERR_INVALID;
+      out_of_place = false;
+    }
+  }
   if (out_of_place && ensure_alt(sv) != QB200_OK) {
     if (sv->swap_mode == 1) return QB200_ERR_OOM;
     out_of_place = false;
@@ -563,31 +610,35 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
     RemapGeom rg{};
     rg.k = k;
     rg.nl = sv->nl;
-    for (unsigned j = 0; j < k; ++j) rg.lbits[j] = sv->pos[victims[j]];
-    const bool vec2 = sv->dtype == QB200_F32 && rg.lbits[0] >= 1;
-    rg.vshift = vec2 ? 1 : 0;
-    rg.items = (uint64_t{1} << sv->nl) >> rg.vshift;
+    // tiles of 2^T amplitudes; tiny shards shrink the tile (at least one 16-byte item per destination run)
+    rg.T = std::min<unsigned>(kTileBits, sv->nl);
+    rg.kl = 0;
+    for (unsigned j = 0; j < k; ++j) {
+      rg.lbits[j] = sv->pos[victims[j]];
+      if (rg.lbits[j] < rg.T) ++rg.kl;
+    }
+    rg.tiles = uint64_t{1} << (sv->nl - rg.T);
+    const size_t smem = (size_t{1} << rg.T) * 2 * scalar_size(sv->dtype);
     const int nb = 1 - sv->cur;
-    timing_begin(sv);
+    timing_mark(sv, 0);
+    timing_mark(sv, 1);  // no leading barrier: the spare buffers are free (see ensure_alt)
     for (auto& s : sv->sh) {
       DevScope d(s.device);
       rg.my = pick_bits(s.rank, gb, k);
       for (unsigned v = 0; v < (1u << k); ++v) rg.dst[v] = sv->peer_buf[nb][with_bits(s.rank, gb, k, v)];
-      uint64_t blocks = (rg.items + 256 * 4 - 1) / (256 * 4);
-      const uint64_t cap = uint64_t{kNumSMs} * 8;
+      uint64_t blocks = rg.tiles;
+      const uint64_t cap = uint64_t{kNumSMs} * 6;
       if (blocks > cap) blocks = cap;
-      if (blocks < 1) blocks = 1;
-      if (sv->dtype == QB200_F32 && vec2)
-        k_remap_push<float4><<<(uint32_t) blocks, 256, 0, s.stream>>>((const float4*) s.buf[sv->cur], rg);
-      else if (sv->dtype == QB200_F32)
-        k_remap_push<float2><<<(uint32_t) blocks, 256, 0, s.stream>>>((const float2*) s.buf[sv->cur], rg);
+      if (sv->dtype == QB200_F32)
+        k_remap_push<float><<<(uint32_t) blocks, kRemapThreads, smem, s.stream>>>((const float*) s.buf[sv->cur], rg);
       else
-        k_remap_push<double2><<<(uint32_t) blocks, 256, 0, s.stream>>>((const double2*) s.buf[sv->cur], rg);
+        k_remap_push<double><<<(uint32_t) blocks, kRemapThreads, smem, s.stream>>>((const double*) s.buf[sv->cur], rg);
       ++s.ctx->launches;
       SV_CUDA(sv, cudaPeekAtLastError());
     }
+    timing_mark(sv, 2);  // (recorded after the launches of every local shard; the first shard's stream only holds its own)
     SV_TRY(barrier(sv));
-    timing_end(sv);
+    timing_mark(sv, 3);
     sv->cur = nb;
     // new map: the remaining local qubits keep their order in the low bits, incoming j sits at nl - k + j
     std::vector<unsigned> vb(rg.lbits, rg.lbits + k);
@@ -625,8 +676,9 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
       std::sort(ord.begin(), ord.end(), [&](unsigned a, unsigned b) { return sv->pos[victims[a]] < sv->pos[victims[b]]; });
       unsigned lb[3], g3[3];
       for (unsigned j = 0; j < kk; ++j) { lb[j] = sv->pos[victims[ord[j]]]; g3[j] = gb[ord[j]]; }
-      timing_begin(sv);
+      timing_mark(sv, 0);
       SV_TRY(barrier(sv));
+      timing_mark(sv, 1);
       for (auto& s : sv->sh) {
         void* peers[8] = {};
         const unsigned my = pick_bits(s.rank, g3, kk);
@@ -634,8 +686,9 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
           if (v != my) peers[v] = sv->peer_buf[sv->cur][with_bits(s.rank, g3, kk, v)];
         SV_TRY(qb200_swap_global_local(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, peers, kk, lb, my));
       }
+      timing_mark(sv, 2);
       SV_TRY(barrier(sv));
-      timing_end(sv);
+      timing_mark(sv, 3);
       for (unsigned j = 0; j < kk; ++j) {
         sv->pos[victims[ord[j]]] = sv->nl + g3[j];
         sv->pos[incoming[ord[j]]] = lb[j];
@@ -797,7 +850,8 @@ int qb200_sv_destroy(qb200_sv* sv) {
     if (s.ctx) qb200_ctx_destroy(s.ctx);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  for (auto& p : sv->ev_pairs) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto& q : sv->ev_quads)
+    for (auto e : q) cudaEventDestroy(e);
   if (sv->err_host) cudaFreeHost(sv->err_host);
   (void) cudaGetLastError();
   delete sv;
@@ -857,6 +911,7 @@ int qb200_sv_get_stats(qb200_sv* sv, qb200_sv_stats* out) {
   out->gate_passes = sv->stats.gate_passes;
   out->bytes_sent_per_shard = sv->stats.bytes_sent_per_shard;
   out->exchange_ms = sv->stats.exchange_ms;
+  out->barrier_wait_ms = sv->stats.wait_ms;
   return QB200_OK;
 }
 
@@ -906,6 +961,18 @@ int qb200_sv_get_ampl(qb200_sv* sv, uint64_t i, double out[2]) {
   out[0] = v[0];
   out[1] = v[1];
   return QB200_OK;
+}
+
+int qb200_sv_get_ampls(qb200_sv* sv, const uint64_t* indices, uint64_t count, double* out) {
+  if (!sv || (count && (!indices || !out))) return QB200_ERR_INVALID;
+  std::fill(out, out + 2 * count, 0.0);
+  for (uint64_t j = 0; j < count; ++j) {
+    if (indices[j] >> sv->n) return QB200_ERR_INVALID;
+    const uint64_t p = to_physical(sv, indices[j]);
+    if (Shard* s = local_shard(sv, (unsigned) (p >> sv->nl)))
+      SV_TRY(qb200_get_ampl(s->ctx, sv->dtype, cur_buf(sv, *s), p & ((uint64_t{1} << sv->nl) - 1), out + 2 * j));
+  }
+  return sum_over_ranks(sv, out, 2 * count);  // one collective for all of them
 }
 
 int qb200_sv_set_ampl(qb200_sv* sv, uint64_t i, double re, double im) {

@@ -68,17 +68,18 @@ def plan(num_qubits: int, num_global: int, ops, global_qubits: Optional[Sequence
 class _TorchComm:
     """qb200_comm over torch.distributed (host buffers; staged through a tensor on `device` for NCCL)."""
 
-    def __init__(self, dist, device):
+    def __init__(self, dist, device, group=None):
         import torch
         self.dist, self.torch, self.device = dist, torch, device
         world = dist.get_world_size()
+        kw = {} if group is None else {"group": group}
 
         def allgather(_user, send, recv, nbytes):
             try:
                 src = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_ubyte)), shape=(nbytes,))
                 t = torch.from_numpy(src.copy()).to(device)
                 outs = [torch.empty_like(t) for _ in range(world)]
-                dist.all_gather(outs, t)
+                dist.all_gather(outs, t, **kw)
                 dst = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_ubyte)), shape=(nbytes * world,))
                 dst[:] = torch.cat(outs).cpu().numpy()
                 return 0
@@ -89,7 +90,7 @@ class _TorchComm:
             try:
                 a = np.ctypeslib.as_array(buf, shape=(count,))
                 t = torch.from_numpy(a.copy()).to(device)
-                dist.all_reduce(t)
+                dist.all_reduce(t, **kw)
                 a[:] = t.cpu().numpy()
                 return 0
             except Exception:
@@ -97,7 +98,7 @@ class _TorchComm:
 
         def barrier(_user):
             try:
-                dist.barrier()
+                dist.barrier(**kw)
                 return 0
             except Exception:
                 return 1
@@ -126,11 +127,16 @@ class ShardedStateB200:
         return cls(h, dtype)
 
     @classmethod
-    def multi_process(cls, dist, num_qubits: int, device_index: int, dtype=np.float32):
+    def multi_process(cls, dist, num_qubits: int, device_index: int, dtype=np.float32, host_group=None):
+        """host_group: a process group whose backend takes CPU tensors (gloo) for the host-side collectives --
+        a few doubles each; without it they are staged through a device tensor of the default (NCCL) group."""
         import torch
         lib = _lib.load()
-        dev = torch.device("cuda", device_index) if dist.get_backend() == "nccl" else torch.device("cpu")
-        comm = _TorchComm(dist, dev)
+        if host_group is not None:
+            comm = _TorchComm(dist, torch.device("cpu"), host_group)
+        else:
+            dev = torch.device("cuda", device_index) if dist.get_backend() == "nccl" else torch.device("cpu")
+            comm = _TorchComm(dist, dev)
         h = C.c_void_p()
         rc = lib.qb200_sv_create_mp(device_index, dist.get_rank(), dist.get_world_size(), C.byref(comm.struct),
                                     num_qubits, _dtype_code(dtype), C.byref(h))
@@ -214,6 +220,13 @@ class ShardedStateB200:
         out = (C.c_double * 2)()
         self._check(self._lib.qb200_sv_get_ampl(self._h, i, out), "GetAmpl")
         return complex(out[0], out[1])
+
+    def GetAmpls(self, indices) -> List[complex]:
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        out = np.zeros(2 * idx.size)
+        self._check(self._lib.qb200_sv_get_ampls(self._h, idx.ctypes.data_as(_lib._pu64), idx.size,
+                                                 out.ctypes.data_as(_lib._pd)), "GetAmpls")
+        return [complex(out[2 * j], out[2 * j + 1]) for j in range(idx.size)]
 
     def SetAmpl(self, i: int, val: complex):
         self._check(self._lib.qb200_sv_set_ampl(self._h, i, complex(val).real, complex(val).imag), "SetAmpl")
