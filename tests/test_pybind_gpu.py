@@ -15,14 +15,25 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def load_module():
-    hits = glob.glob(os.path.join(ROOT, "qsim_b200", "qsim_b200_py*.so"))
+_LOADED = {}
+
+
+def load_module(name="qsim_b200_py"):
+    if name in _LOADED:
+        return _LOADED[name]
+    hits = glob.glob(os.path.join(ROOT, "qsim_b200", name + ".*.so"))
     if not hits:
         pytest.skip("pybind extension not built (needs the reference tree at build time)")
-    spec = importlib.util.spec_from_file_location("qsim_b200_py", hits[0])
+    spec = importlib.util.spec_from_file_location(name, hits[0])
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    _LOADED[name] = mod
     return mod
+
+
+# qsim_b200_py: single-GPU backend; qsim_b200_sharded_py: state sharded over "gnd" GPUs through B200Runner
+# (pybind/pybind_main_b200_sharded.cpp) -- with one GPU in the box the four shards share it
+MODULES = [("qsim_b200_py", {}), ("qsim_b200_sharded_py", {"gnd": 4})]
 
 
 H = (np.array([[1, 1], [1, -1]]) / np.sqrt(2)).astype(np.complex64)
@@ -69,36 +80,42 @@ def options(c, **kw):
     return o
 
 
-def test_fullstate_amplitudes_and_samples(oracle):
-    q = load_module()
+@pytest.mark.parametrize("module,extra", MODULES)
+def test_fullstate_amplitudes_and_samples(oracle, module, extra):
+    q0 = load_module()          # circuit classes + builders live in the base module, as with qsimcirq
+    q = load_module(module)
     n = 14
-    c, want = build(q, n, oracle)
+    c, want = build(q0, n, oracle)
+    opt = lambda c, **kw: options(c, **dict(extra, **kw))  # noqa: E731 -- the module's own options on every call
     for f in (2, 4):
-        got = np.asarray(q.qsim_simulate_fullstate(options(c, f=f), 0)).view(np.complex64)
+        got = np.asarray(q.qsim_simulate_fullstate(opt(c, f=f), 0)).view(np.complex64)
         assert got.shape == want.shape
         assert np.abs(got - want).max() < 2e-6
     # amplitudes of chosen bitstrings (qsim_simulate): the string's first character is qubit 0
     idx = [0, 1, 5, (1 << n) - 1, 12345 % (1 << n)]
     strings = "\n".join("".join("1" if (i >> b) & 1 else "0" for b in range(n)) for i in idx)
-    amps = np.asarray(q.qsim_simulate(options(c, i=strings)))
+    amps = np.asarray(q.qsim_simulate(opt(c, i=strings)))
     assert np.abs(amps - want[idx]).max() < 2e-6
     # an initial state handed in as a vector, and one handed in as a basis-state index
     init = np.zeros(2 << n, np.float32)
     init[2 * 3] = 1.0
-    a = np.asarray(q.qsim_simulate_fullstate(options(c), init)).view(np.complex64)
-    b = np.asarray(q.qsim_simulate_fullstate(options(c), 3)).view(np.complex64)
+    a = np.asarray(q.qsim_simulate_fullstate(opt(c), init)).view(np.complex64)
+    b = np.asarray(q.qsim_simulate_fullstate(opt(c), 3)).view(np.complex64)
     assert np.abs(a - b).max() < 1e-6 and abs(np.vdot(a, a).real - 1) < 1e-5
 
 
-def test_expectation_values(oracle):
-    q = load_module()
+@pytest.mark.parametrize("module,extra", MODULES)
+def test_expectation_values(oracle, module, extra):
+    q0 = load_module()
+    q = load_module(module)
     n = 10
-    c, want = build(q, n, oracle)
-    s = q.OpString()
+    c, want = build(q0, n, oracle)
+    opt = lambda c, **kw: options(c, **dict(extra, **kw))  # noqa: E731
+    s = q0.OpString()
     s.weight = 1.0
-    q.add_gate_to_opstring(q.GateKind.kZ, [2], s)
-    q.add_gate_to_opstring(q.GateKind.kX, [7], s)
-    got = q.qsim_simulate_expectation_values(options(c), [([s], 2)], 0)[0]
+    q0.add_gate_to_opstring(q0.GateKind.kZ, [2], s)
+    q0.add_gate_to_opstring(q0.GateKind.kX, [7], s)
+    got = q.qsim_simulate_expectation_values(opt(c), [([s], 2)], 0)[0]
     z = np.array([[1, 0], [0, -1]], np.complex64)
     x = np.array([[0, 1], [1, 0]], np.complex64)
     ket = want.copy()
