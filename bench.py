@@ -484,12 +484,12 @@ def main():
     # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_g4_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             tj = json.load(f)
         key = next(k for k in tj["kernels"] if dom.startswith(k.split("<")[0] + "<") and k.split("<")[1][0] == dom.split("<")[1][0])
         k = tj["kernels"][key]
         traffic = (k["dram_bytes_read"] + k["dram_bytes_write"]) * (amps / float(1 << 30))
-        traffic_src = f"profiles/r01_ncu_g4_traffic.json [{key}] (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+        traffic_src = f"profiles/r02_ncu_traffic.json [{key}] (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
