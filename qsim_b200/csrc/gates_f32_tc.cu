@@ -103,7 +103,8 @@ int launch_tcx_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m, d
   int rc = stage_matrix(ctx, m, sizeof(float) * (size_t{2} << (2 * G)), &dmat);
   if (rc) return rc;
   // accumulation-bias compensation (see tc_bias): measured per G; none for expectation values
-  const float comp = EXPECT ? 0.f : (G == 4 ? tc_bias<4>() : G == 5 ? tc_bias<5>() : (float) ctx->tune.tc_comp6 * 1e-9f);
+  const float comp = EXPECT || is_monomial(m, G) ? 0.f
+                   : (G == 4 ? tc_bias<4>() : G == 5 ? tc_bias<5>() : (float) ctx->tune.tc_comp6 * 1e-9f);
   kern<<<blocks, kTcThreads, smem, ctx->stream>>>(st, g, (const float*) dmat, comp, partials);
   QB_LAUNCHED(ctx);
   stage_matrix_done(ctx);
@@ -112,6 +113,25 @@ int launch_tcx_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m, d
 }
 
 }  // namespace
+
+// At most one non-zero per row and per column: permutations, Pauli strings, diagonal phases, CZ/SWAP-like fused
+// gates.  Every output amplitude is then ONE product, there is no accumulation whose truncation the compensation
+// term was calibrated to cancel (tc_bias: mean norm drift of DENSE unitaries), so for these matrices the term
+// would inflate the norm by ~1e-7 per pass.  Without it a permutation with entries in {0, +-1, +-i} is exact on the
+// tensor cores (A_hi + A_lo == A in fp32).
+static bool is_monomial(const float* m, unsigned nq) {
+  const unsigned dim = 1u << nq;
+  unsigned col_used[64] = {};
+  for (unsigned r = 0; r < dim; ++r) {
+    unsigned nz = 0;
+    for (unsigned c = 0; c < dim; ++c) {
+      if (m[2 * (r * dim + c)] != 0.f || m[2 * (r * dim + c) + 1] != 0.f) {
+        if (++nz > 1 || col_used[c]++) return false;
+      }
+    }
+  }
+  return true;
+}
 
 int launch_tcx_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool pair, const float* m,
                    bool expect, double* out) {
@@ -127,11 +147,14 @@ int launch_tcx_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool p
 
 int launch_tc_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool pair, const float* m) {
   const bool alt = ctx->tune.tc == 2;  // alternative shapes (tools/tc_check.py)
-  if (ctx->tune.tc < 0 || ctx->tune.tc == 3) {  // default: A operand in tensor memory, bias-compensated
+  // default: A operand in tensor memory, bias-compensated -- except for matrices with one non-zero per row
+  // (is_monomial): plain 3xTF32, which is exact for permutations
+  const bool plain = ctx->tune.tc == 4 || ((ctx->tune.tc < 0 || ctx->tune.tc == 3) && is_monomial(m, nq));
+  if (!plain && (ctx->tune.tc < 0 || ctx->tune.tc == 3)) {
     if (nq == 4) return pair ? launch_tca_shape<4, true, 1, 2, 1, true, 0, 3>(ctx, st, g, m) : launch_tca_shape<4, false, 1, 2, 1, true, 0, 3>(ctx, st, g, m);
     if (nq == 5) return pair ? launch_tca_shape<5, true, 1, 1, 1, true, 0, 2>(ctx, st, g, m) : launch_tca_shape<5, false, 1, 1, 1, true, 0, 2>(ctx, st, g, m);
   }
-  if (ctx->tune.tc == 4) {  // ... without the compensation term (plain 3xTF32)
+  if (plain) {  // ... without the compensation term (plain 3xTF32)
     if (nq == 4) return pair ? launch_tca_shape<4, true, 1, 2, 1, false, 0, 3>(ctx, st, g, m) : launch_tca_shape<4, false, 1, 2, 1, false, 0, 3>(ctx, st, g, m);
     if (nq == 5) return pair ? launch_tca_shape<5, true, 1, 1, 1, false, 0, 2>(ctx, st, g, m) : launch_tca_shape<5, false, 1, 1, 1, false, 0, 2>(ctx, st, g, m);
   }

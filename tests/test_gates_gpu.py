@@ -467,3 +467,57 @@ def test_tensor_core_6_qubit_gate_norm_drift():
         qs = sorted(rng.choice(np.arange(3, n), 6, replace=False).tolist())
         sim.ApplyGate(qs, random_unitary(6, i, np.complex64), st)
     assert abs(ss.Norm(st) - 1.0) < 16 * 1e-7
+
+
+def _structured_matrices(g, seed):
+    """permutation with phases in {+-1, +-i}, diagonal phases, identity, a Pauli string: one non-zero per row"""
+    rng = np.random.default_rng(seed)
+    dim = 1 << g
+    perm = np.zeros((dim, dim), np.complex64)
+    perm[np.arange(dim), rng.permutation(dim)] = rng.choice(np.array([1, -1, 1j, -1j], np.complex64), dim)
+    diag = np.diag(np.exp(1j * rng.uniform(0, 2 * np.pi, dim))).astype(np.complex64)
+    ident = np.eye(dim, dtype=np.complex64)
+    p = {"X": np.array([[0, 1], [1, 0]]), "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.diag([1, -1])}
+    pauli = np.array([[1.0]])
+    for c in rng.choice(list("XYZ"), g):
+        pauli = np.kron(p[c], pauli)
+    return {"permutation": perm, "diagonal": diag, "identity": ident, "pauli": pauli.astype(np.complex64)}
+
+
+@pytest.mark.parametrize("g", [4, 5, 6])
+def test_tensor_core_path_on_structured_matrices_and_sparse_states(oracle, g):
+    """the accumulation-bias compensation of the tensor-core kernels was fitted on dense unitaries and
+    dense states.  Matrices with one non-zero per row get none (gates_f32_tc.cu is_monomial): on basis states and
+    on dense states, 100 passes of permutations / Pauli strings / identities leave the state EXACT (bit for bit
+    against the oracle), diagonal phases keep the norm to 1e-6."""
+    import qsim_b200
+    ss, sim = qsim_b200.StateSpaceB200(np.float32), qsim_b200.SimulatorB200(np.float32)
+    n = 18
+    mats = _structured_matrices(g, g)
+    rng = np.random.default_rng(100 + g)
+    for start in ("basis", "dense"):
+        for name, m in mats.items():
+            host = np.zeros(1 << n, np.complex64)
+            if start == "basis":
+                host[12345] = 1
+            else:
+                host = random_state(n, np.complex64, seed=5)
+            st = ss.Create(n)
+            ss.from_numpy(host, st)
+            want = host.copy()
+            for it in range(100):
+                qs = sorted(rng.choice(np.arange(4 if it % 2 else 0, n), g, replace=False).tolist())
+                sim.ApplyGate(qs, m, st)
+                assert sim.last_kernel_name().startswith("k_gate_tc"), sim.last_kernel_name()
+                if name != "diagonal" and it < 12:
+                    oracle.apply_gate(want, qs, m)
+                    if it == 11:
+                        assert np.array_equal(ss.to_numpy(st), want), (start, name)
+            assert abs(ss.Norm(st) - 1.0) < 1e-6, (start, name, ss.Norm(st))
+    # dense unitaries on a basis state (the first passes of every circuit): the compensated path keeps the norm
+    st = ss.Create(n)
+    ss.SetStateZero(st)
+    for it in range(60):
+        qs = sorted(rng.choice(np.arange(n), g, replace=False).tolist())
+        sim.ApplyGate(qs, random_unitary(g, it, np.complex64), st)
+    assert abs(ss.Norm(st) - 1.0) < 60 * 2e-7
