@@ -9,6 +9,25 @@ namespace qb200 {
 
 namespace {
 
+// At most one non-zero per row and per column: permutations, Pauli strings, diagonal phases, CZ/SWAP-like fused
+// gates.  Every output amplitude is then ONE product, there is no accumulation whose truncation the compensation
+// term was calibrated to cancel (tc_bias: mean norm drift of DENSE unitaries), so for these matrices the term
+// would inflate the norm by ~1e-7 per pass.  Without it a permutation with entries in {0, +-1, +-i} is exact on the
+// tensor cores (A_hi + A_lo == A in fp32).
+static bool is_monomial(const float* m, unsigned nq) {
+  const unsigned dim = 1u << nq;
+  unsigned col_used[64] = {};
+  for (unsigned r = 0; r < dim; ++r) {
+    unsigned nz = 0;
+    for (unsigned c = 0; c < dim; ++c) {
+      if (m[2 * (r * dim + c)] != 0.f || m[2 * (r * dim + c) + 1] != 0.f) {
+        if (++nz > 1 || col_used[c]++) return false;
+      }
+    }
+  }
+  return true;
+}
+
 template <int G, bool PAIR, int NBUF, int PF, int MINB>
 int launch_tc_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
   auto kern = k_gate_tc<G, PAIR, NBUF, PF, MINB>;
@@ -113,25 +132,6 @@ int launch_tcx_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m, d
 }
 
 }  // namespace
-
-// At most one non-zero per row and per column: permutations, Pauli strings, diagonal phases, CZ/SWAP-like fused
-// gates.  Every output amplitude is then ONE product, there is no accumulation whose truncation the compensation
-// term was calibrated to cancel (tc_bias: mean norm drift of DENSE unitaries), so for these matrices the term
-// would inflate the norm by ~1e-7 per pass.  Without it a permutation with entries in {0, +-1, +-i} is exact on the
-// tensor cores (A_hi + A_lo == A in fp32).
-static bool is_monomial(const float* m, unsigned nq) {
-  const unsigned dim = 1u << nq;
-  unsigned col_used[64] = {};
-  for (unsigned r = 0; r < dim; ++r) {
-    unsigned nz = 0;
-    for (unsigned c = 0; c < dim; ++c) {
-      if (m[2 * (r * dim + c)] != 0.f || m[2 * (r * dim + c) + 1] != 0.f) {
-        if (++nz > 1 || col_used[c]++) return false;
-      }
-    }
-  }
-  return true;
-}
 
 int launch_tcx_f32(qb200_ctx* ctx, float* st, const Geom& g, unsigned nq, bool pair, const float* m,
                    bool expect, double* out) {
