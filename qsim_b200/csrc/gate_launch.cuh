@@ -250,18 +250,21 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
 
   // fp32 G = 4, 5 gates: tcgen05 3xTF32 kernel (gate_tc.cuh); tiles of 128 groups
   if constexpr (sizeof(FP) == 4 && !EXPECT) {
-    // auto (-1): every G = 5 pass (2.7 ms against 5.95 ms on the CUDA cores at n = 30) and the G = 4
-    // passes whose per-thread row pieces form runs of >= 32 contiguous bytes across neighbouring lanes;
-    // measured per layout (profiles/r01_tc_check.txt): lowest target >= 4, or 2, or 3 with the next
-    // one above bit 4, or bit 0 together with anything but {1, 2}.  The rest ([0,1,2,..], lowest
-    // target 1, [3,4,..]) is faster on the warp-tile / cp.async FFMA2 kernels.  tc_low >= 0 replaces
-    // the rule by a plain threshold on the lowest non-zero target (experiments).
+    // auto (-1): every G = 5 pass (the tensor-core kernel wins for all 32 low-bit layouts, 0.33-0.9x the time of
+    // k_gate_big<5>) and every G = 4 pass except the layouts with at least two targets on bits 1, 2, 3: what decides
+    // is which targets sit inside the warp's lane bits 0..4 (the per-thread row pieces then form short runs across
+    // neighbouring lanes), not the qubit count of the state -- the same 15 of 31 masks lose by 2-110 % at n = 26, 30
+    // and 33 (tools/dispatch_sweep.py, profiles/r02_dispatch_sweep.txt) and go to the warp-tile FFMA2 kernel below.
+    // tc_low >= 0 replaces the table by a plain threshold on the lowest non-zero target (experiments).
     bool g4_tc = false;
     if (nq == 4) {
       if (ctx->tune.tc_low >= 0) {
         g4_tc = (int) (qs[0] == 0 ? qs[1] : qs[0]) >= ctx->tune.tc_low;
       } else {
-        g4_tc = qs[0] >= 4 || qs[0] == 2 || (qs[0] == 3 && qs[1] > 4) || (qs[0] == 0 && !(qs[1] == 1 && qs[2] == 2));
+        unsigned low_mask = 0;
+        for (unsigned j = 0; j < nq; ++j)
+          if (qs[j] < 5) low_mask |= 1u << qs[j];
+        g4_tc = __builtin_popcount(low_mask & 0b01110u) < 2;
       }
     }
     const bool use_tc = ctx->tune.tc > 0 || (ctx->tune.tc < 0 && (nq == 5 || g4_tc));

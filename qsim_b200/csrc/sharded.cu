@@ -113,6 +113,144 @@ k_remap_push(const FP* __restrict__ src, const __grid_constant__ RemapGeom g) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The same exchange with the bulk-copy engine (TMA) on both ends of the tile: one thread issues
+// cp.async.bulk.shared::cluster.global for the next 16 KB tile (mbarrier complete_tx), the CTA's threads only do the
+// shared->shared scatter that sorts the tile by its victim bits, and one thread issues one
+// cp.async.bulk.global.shared::cta per destination run (>= 2 KB, straight into the peer's buffer).  Two input and two
+// output stages per CTA: 64 KB in flight per CTA without holding registers or warps, so the kernel needs few threads --
+// which is what lets gate kernels run beside it.
+// ---------------------------------------------------------------------------------------------------------
+namespace bulk {
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" ::"r"(mbar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void store(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace bulk
+
+template <typename FP>
+__global__ void __launch_bounds__(kRemapThreads)
+k_remap_push_tma(const FP* __restrict__ src, const __grid_constant__ RemapGeom g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[2];
+  constexpr int APT = sizeof(FP) == 4 ? 2 : 1;
+  const uint32_t tile_amps = 1u << g.T;
+  const uint32_t tile_bytes = tile_amps * 2 * sizeof(FP);
+  const uint32_t items = tile_amps / APT;
+  const uint32_t kh = g.k - g.kl;
+  const uint32_t sub_bits = g.T - g.kl;
+  const uint32_t my_high = g.my >> g.kl;
+  unsigned char* const in_p = smem_raw;                       // 2 input stages
+  unsigned char* const out_p = smem_raw + 2 * tile_bytes;     // 2 output stages
+  const uint32_t in_s = bulk::smem_addr(in_p), out_s = bulk::smem_addr(out_p);
+  const uint32_t full_s = bulk::smem_addr(&full[0]);
+  if (threadIdx.x == 0) {
+    bulk::mbar_init(full_s, 1);
+    bulk::mbar_init(full_s + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto tile_index = [&](uint64_t c, uint32_t* v_high) {
+    *v_high = ((uint32_t) c & ((1u << kh) - 1)) ^ my_high;
+    uint64_t tau = c >> kh;
+    for (uint32_t j = g.kl; j < g.k; ++j) {
+      const uint32_t b = g.lbits[j] - g.T;
+      const uint64_t lo = tau & ((uint64_t{1} << b) - 1);
+      tau = (((tau >> b) << 1 | ((*v_high >> (j - g.kl)) & 1)) << b) | lo;
+    }
+    return tau;
+  };
+
+  uint64_t c = blockIdx.x;
+  if (threadIdx.x == 0 && c < g.tiles) {
+    uint32_t vh;
+    const uint64_t tau = tile_index(c, &vh);
+    bulk::mbar_expect_tx(full_s, tile_bytes);
+    bulk::load(in_s, reinterpret_cast<const unsigned char*>(src) + tau * tile_bytes, tile_bytes, full_s);
+  }
+  for (uint32_t it = 0; c < g.tiles; c += gridDim.x, ++it) {
+    const uint32_t s = it & 1;
+    if (threadIdx.x == 0) {
+      const uint64_t cn = c + gridDim.x;
+      if (cn < g.tiles) {  // input stage s^1 was consumed by the scatter of the previous iteration
+        uint32_t vh;
+        const uint64_t tau = tile_index(cn, &vh);
+        bulk::mbar_expect_tx(full_s + 8 * (s ^ 1), tile_bytes);
+        bulk::load(in_s + (s ^ 1) * tile_bytes, reinterpret_cast<const unsigned char*>(src) + tau * tile_bytes, tile_bytes,
+                   full_s + 8 * (s ^ 1));
+      }
+      bulk::wait_read<1>();  // the stores issued two iterations ago have read output stage s
+    }
+    __syncthreads();
+    bulk::mbar_wait(full_s + 8 * s, (it >> 1) & 1);
+    const unsigned char* const tin = in_p + s * tile_bytes;
+    unsigned char* const tout = out_p + s * tile_bytes;
+    for (uint32_t i0 = threadIdx.x; i0 < items; i0 += kRemapThreads) {
+      const uint4 x = reinterpret_cast<const uint4*>(tin)[i0];
+#pragma unroll
+      for (int a = 0; a < APT; ++a) {
+        uint32_t i = i0 * APT + a, v = 0, r = i;
+        for (int j = (int) g.kl - 1; j >= 0; --j) {
+          const uint32_t b = g.lbits[j];
+          v |= ((r >> b) & 1u) << j;
+          r = ((r >> (b + 1)) << b) | (r & ((1u << b) - 1));
+        }
+        const uint32_t p = (v << sub_bits) | r;
+        if constexpr (APT == 2) {
+          reinterpret_cast<uint2*>(tout)[p] = a == 0 ? make_uint2(x.x, x.y) : make_uint2(x.z, x.w);
+        } else {
+          reinterpret_cast<uint4*>(tout)[p] = x;
+        }
+      }
+    }
+    bulk::fence_async();   // generic-proxy writes to shared memory -> visible to the bulk-copy engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t v_high;
+      (void) tile_index(c, &v_high);
+      const uint64_t packed_high = c >> kh;
+      const uint32_t run_bytes = (1u << sub_bits) * 2 * sizeof(FP);
+      const uint64_t d = ((uint64_t{g.my} << (g.nl - g.k)) | (packed_high << sub_bits)) * 2 * sizeof(FP);
+      for (uint32_t vl = 0; vl < (1u << g.kl); ++vl) {
+        const uint32_t v = vl | (v_high << g.kl);
+        bulk::store(reinterpret_cast<unsigned char*>(g.dst[v]) + d, out_s + s * tile_bytes + vl * run_bytes, run_bytes);
+      }
+      bulk::commit();
+    }
+  }
+  if (threadIdx.x == 0) bulk::wait_all();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // flag barrier between shards that live in different processes: shard `me` writes the epoch into its slot of
 // every peer's flag array (release, system scope) and waits until all its own slots carry it.  One warp.
 // A peer that never arrives trips the timeout instead of hanging the GPU; the error word is mapped host memory.
@@ -199,6 +337,8 @@ struct qb200_sv {
   int barrier_flags = 0;                 // 1: flag kernels (always in mp mode); 0: events
   int swap_mode = -1;                    // -1 auto (out of place when the second buffer fits), 0 in place, 1 out of place
   int reorder = 1;
+  int push_kernel = 1;                   // 1: bulk-copy engine (k_remap_push_tma, default); 0: st.global from registers
+  int push_ctas_per_sm = 0;              // 0 = default of the chosen kernel
   SvStats stats;
   std::vector<uint64_t> plan_key;        // gate structure + global set the cached schedule was made for
   std::vector<int64_t> plan_steps;
@@ -629,7 +769,26 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
       uint64_t blocks = rg.tiles;
       const uint64_t cap = uint64_t{kNumSMs} * 6;
       if (blocks > cap) blocks = cap;
-      if (sv->dtype == QB200_F32)
+      if (sv->push_kernel == 1) {
+        // bulk-copy variant: 2 + 2 stages of one tile each; opt in to the shared memory once per device
+        const size_t smem4 = 4 * smem;
+        static PerDevice attr_f, attr_d;
+        if (sv->dtype == QB200_F32) {
+          attr_f.get(s.ctx, [&] {
+            cudaFuncSetAttribute(k_remap_push_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16384);
+            return 1;
+          });
+          uint64_t b2 = std::min<uint64_t>(rg.tiles, uint64_t{kNumSMs} * (sv->push_ctas_per_sm > 0 ? sv->push_ctas_per_sm : 3));
+          k_remap_push_tma<float><<<(uint32_t) b2, kRemapThreads, smem4, s.stream>>>((const float*) s.buf[sv->cur], rg);
+        } else {
+          attr_d.get(s.ctx, [&] {
+            cudaFuncSetAttribute(k_remap_push_tma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768);
+            return 1;
+          });
+          uint64_t b2 = std::min<uint64_t>(rg.tiles, uint64_t{kNumSMs} * (sv->push_ctas_per_sm > 0 ? sv->push_ctas_per_sm : 1));
+          k_remap_push_tma<double><<<(uint32_t) b2, kRemapThreads, smem4, s.stream>>>((const double*) s.buf[sv->cur], rg);
+        }
+      } else if (sv->dtype == QB200_F32)
         k_remap_push<float><<<(uint32_t) blocks, kRemapThreads, smem, s.stream>>>((const float*) s.buf[sv->cur], rg);
       else
         k_remap_push<double><<<(uint32_t) blocks, kRemapThreads, smem, s.stream>>>((const double*) s.buf[sv->cur], rg);
@@ -885,6 +1044,8 @@ int qb200_sv_set_option(qb200_sv* sv, const char* key, int value) {
   if (!sv || !key) return QB200_ERR_INVALID;
   if (!std::strcmp(key, "swap_mode")) sv->swap_mode = value;
   else if (!std::strcmp(key, "reorder")) sv->reorder = value;
+  else if (!std::strcmp(key, "push_kernel")) sv->push_kernel = value;
+  else if (!std::strcmp(key, "push_ctas_per_sm")) sv->push_ctas_per_sm = value;
   else if (!std::strcmp(key, "barrier_flags")) {
     if (sv->mp && !value) return QB200_ERR_INVALID;  // events do not cross processes
     sv->barrier_flags = value;

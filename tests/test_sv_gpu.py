@@ -49,7 +49,7 @@ def logical_from_physical(phys_state, pos):
 
 
 @pytest.mark.parametrize("shards", [2, 4, 8])
-@pytest.mark.parametrize("swap_mode", [1, 0])
+@pytest.mark.parametrize("swap_mode", [1, 0, "tma"])
 @pytest.mark.parametrize("barrier_flags", [0, 1])
 def test_exchange_is_an_exact_index_permutation(shards, swap_mode, barrier_flags):
     """qb200_sv_swap for k = 1..g victims at low / high / mixed local bits: the logical state is unchanged bit
@@ -58,7 +58,9 @@ def test_exchange_is_an_exact_index_permutation(shards, swap_mode, barrier_flags
     n = 12 + g
     nl = n - g
     want = random_state(n, np.complex64, 5)
-    st = make(shards, n, swap_mode=swap_mode, barrier_flags=barrier_flags)
+    opts = {"swap_mode": 1, "push_kernel": 1} if swap_mode == "tma" else {"swap_mode": swap_mode}  # bulk-copy push kernel
+    swap_mode = 1 if swap_mode == "tma" else swap_mode
+    st = make(shards, n, barrier_flags=barrier_flags, **opts)
     st.from_numpy(want)
     rng = np.random.default_rng(shards * 10 + swap_mode)
     cases = [[0], [nl - 1], [1, 2, 3][:g], [nl - 1, nl - 2, nl - 3][:g], [0, 5, nl - 1][:g], [3]]
@@ -146,14 +148,16 @@ def test_run_matches_unsharded_oracle(oracle, shards, swap_mode, reorder):
     st.close(); st2.close()
 
 
-def test_run_fp64(oracle):
+@pytest.mark.parametrize("push_kernel", [0, 1])
+def test_run_fp64(oracle, push_kernel):
     n, shards = 13, 4
     ops = random_ops(n, 40, seed=3, max_targets=5)
     want = oracle_run(oracle, n, ops, np.complex128)
-    st = make(shards, n, np.float64)
+    st = make(shards, n, np.float64, push_kernel=push_kernel)
     st.SetStateZero()
     st.Run(ops)
     assert np.abs(st.to_numpy() - want).max() < 1e-13
+    assert st.stats()["swaps"] >= 1
     st.close()
 
 

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--tune", action="append", default=[])
     ap.add_argument("--out", default=None)
     ap.add_argument("--statespace", action="store_true")
+    ap.add_argument("--controlled", action="store_true", help="controlled-gate sweep (C = 1..3, low/high/mixed controls)")
     args = ap.parse_args()
     rdt, cdt = (np.float32, np.complex64) if args.dtype == "f32" else (np.float64, np.complex128)
     ss, sim = qsim_b200.StateSpaceB200(rdt), qsim_b200.SimulatorB200(rdt)
@@ -74,14 +75,28 @@ def main():
             u = unitary(g, g, cdt)
             med, best = timeit(lambda: sim.ApplyGate(qs, u, st), args.reps)
             emit({"op": "gate", "n": n, "dtype": args.dtype, "G": g, "layout": name, "qs": qs, "ms": med, "ms_min": best,
-                  "GBps": pass_bytes / med / 1e6, "tune": args.tune})
-    # controlled gates and expectation values
-    for g, qs, cqs in ((2, [12, 20], [25]), (2, [0, 20], [1]), (4, [8, 9, 14, 15], [3, 22])):
-        if max(qs + cqs) >= n:
-            continue
-        u = unitary(g, g, cdt)
-        med, best = timeit(lambda: sim.ApplyControlledGate(qs, cqs, (1 << len(cqs)) - 1, u, st), args.reps)
-        emit({"op": "cgate", "n": n, "G": g, "qs": qs, "cqs": cqs, "ms": med, "GBps": pass_bytes / (1 << len(cqs)) / med / 1e6})
+                  "GBps": pass_bytes / med / 1e6, "kernel": sim.last_kernel_name(), "tune": args.tune})
+    # controlled gates: C = 1, 2, 3 controls on low / high / mixed bits, control values all ones and all
+    # zeros, under targets of 1, 2 and 4 qubits (low and high).  Algorithmic bytes = 16 * 2^(n - C).
+    ctl_sets = {1: {"low": [1], "high": [n - 2], "mixed": [6]},
+                2: {"low": [1, 2], "high": [n - 3, n - 2], "mixed": [2, n - 2]},
+                3: {"low": [1, 2, 4], "high": [n - 4, n - 3, n - 2], "mixed": [1, 11, n - 2]}}
+    tgt_sets = {1: {"low": [0], "high": [n - 1], "mid": [9]},
+                2: {"low": [0, 3], "high": [n - 5, n - 1], "mid": [8, 13]},
+                4: {"low": [0, 3, 5, 7], "high": [n - 9, n - 7, n - 5, n - 1], "mid": [8, 9, 14, 15]}}
+    if args.controlled:
+        for g, tsets in tgt_sets.items():
+            u = unitary(g, g, cdt)
+            for tname, qs in tsets.items():
+                for c, csets in ctl_sets.items():
+                    for cname, cqs in csets.items():
+                        if set(qs) & set(cqs) or max(qs + cqs) >= n:
+                            continue
+                        for cv_name, cv in (("ones", (1 << c) - 1), ("zeros", 0)):
+                            med, best = timeit(lambda: sim.ApplyControlledGate(qs, cqs, cv, u, st), args.reps)
+                            emit({"op": "cgate", "n": n, "G": g, "targets": tname, "C": c, "controls": cname, "cvals": cv_name,
+                                  "qs": qs, "cqs": cqs, "ms": med, "kernel": sim.last_kernel_name(),
+                                  "GBps": pass_bytes / (1 << c) / med / 1e6})
     sim2 = qsim_b200.SimulatorB200(rdt)
     for g, qs in ((1, [7]), (2, [3, 19]), (4, [8, 9, 14, 15]), (5, [0, 3, 7, 12, 20]), (6, [1, 5, 9, 13, 17, 21])):
         if max(qs) >= n:

@@ -34,6 +34,9 @@ else:
     g = world.bit_length() - 1
     sv = ShardedStateB200.multi_process(dist, n_local + g, local)
 n = n_local + g
+for kv in os.environ.get("QB200_SV_OPTIONS", "").split(","):   # e.g. push_kernel=1,push_ctas_per_sm=2
+    if kv:
+        sv.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 sv.SetStateUniform()
 cases = []
 for k in range(1, g + 1):
