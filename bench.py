@@ -42,6 +42,37 @@ def emit(line):
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
+def sustained_copy_gbs(seconds=1.5):
+    """Copy bandwidth of THIS box in steady state, for context beside MEASURED_PEAKS.json (a best-of-10 burst): a
+    2 GiB device-to-device torch copy repeated back to back for ~1.5 s (read + write bytes, CUDA events) -- what a
+    plain copy sustains once the board sits at its power cap, like the 41 passes of a step do."""
+    try:
+        import torch
+        a = torch.empty(1 << 29, dtype=torch.float32, device="cuda")
+        b = torch.empty_like(a)
+        for _ in range(3):
+            b.copy_(a)
+        torch.cuda.synchronize()
+        reps = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        while True:
+            for _ in range(20):
+                b.copy_(a)
+            reps += 20
+            torch.cuda.synchronize()
+            if time.perf_counter() - t0 > seconds:
+                break
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        del a, b
+        return 2.0 * 4 * (1 << 29) * reps / (ms * 1e-3) / 1e9
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -249,9 +280,9 @@ def run_sharded(args, rank, world, local_rank, dist):
     clocks = sampler.stop() if rank == 0 else None
     launches = sv.launch_count() - l0
     stats = sv.stats()
-    t = torch.tensor([dev_ms, stats["exchange_ms"]], device="cuda", dtype=torch.float64)
+    t = torch.tensor([dev_ms, stats["exchange_ms"], stats["overlap_ms"]], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, exch_ms = float(t[0].item()), float(t[1].item())
+    dev_ms, exch_ms, ovl_ms = float(t[0].item()), float(t[1].item()), float(t[2].item())
     ms_per_step = dev_ms / args.steps
     total_bytes = len(ops) * 16.0 * (1 << n)
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
@@ -317,7 +348,14 @@ def run_sharded(args, rank, world, local_rank, dist):
                 "swap": {"swaps_per_circuit": swaps, "bytes_sent_per_rank_per_circuit": sent,
                          "exchange_ms_per_circuit": exch_ms / args.steps,
                          "barrier_wait_ms_per_circuit_rank0": stats["barrier_wait_ms"] / args.steps,
-                         "nvlink_GBps_per_direction": sent / (exch_ms / args.steps * 1e-3) / 1e9 if exch_ms > 0 else None,
+                         "overlapped_exchanges_per_circuit": int(stats["overlapped_swaps"]) // args.steps,
+                         "gate_passes_pipelined_against_them": int(stats["overlapped_gate_passes"]) // args.steps,
+                         "overlapped_pipeline_ms_per_circuit": ovl_ms / args.steps,
+                         "note": "an overlapped exchange runs chunk by chunk on a second stream beside the last gate passes of its "
+                                 "epoch (csrc/sharded.cu run_overlapped); its time is inside overlapped_pipeline_ms (gates included), "
+                                 "exchange_ms covers the exchanges that ran alone",
+                         "nvlink_GBps_per_direction": (sent / (exch_ms / args.steps * 1e-3) / 1e9
+                                                       if exch_ms > 0 and not stats["overlapped_swaps"] else None),
                          "nvlink_peak_GBps_per_direction": 900.0},
                 "parity": parity,
                 "cpu_baseline": None,
@@ -492,7 +530,11 @@ def main():
         traffic_src = f"profiles/r02_ncu_traffic.json [{key}] (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
     except Exception:
         pass
+    sustained = sustained_copy_gbs()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "sustained_copy_GBps_this_box": sustained,
+                "frac_of_sustained_copy": achieved / sustained if sustained else None,
+                "whole_step_frac": value / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": pass_bytes,
                 "kernel": dom, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                 "avg_launch_ms": dom_ms, "launches_timed": kernels[dom]["launches"],

@@ -77,6 +77,9 @@ const char* qb200_last_kernel_name(const qb200_ctx* ctx);
 /* Persistent grids of this context are sized for `sms` SMs instead of all 148 (0 = all): used while an
  * exchange kernel of a sharded state owns the remaining SMs (csrc/sharded.cu). */
 int qb200_ctx_set_sm_limit(qb200_ctx* ctx, int sms);
+/* Persistent grids of this context count on `ctas_per_sm` fewer resident CTAs per SM (0 = all): set while an exchange
+ * kernel runs beside the gates and holds registers, threads and shared memory on every SM. */
+int qb200_ctx_set_occupancy_reduction(qb200_ctx* ctx, int ctas_per_sm);
 /* Kernel-selection overrides for experiments and for the cross-check tests (defaults = -1 = auto):
  *   gate_mode 0      one amplitude per access in the register kernels
  *   force_generic 1  runtime-generic kernel for everything
@@ -141,8 +144,9 @@ int qb200_apply_controlled_gate(qb200_ctx* ctx, int dtype, void* state, unsigned
  * tensor core's truncating accumulation loses ~1.7e-7 (G=4) .. 5.5e-7 (G=6) of the norm per pass on dense
  * unitaries, which a fitted compensation term cancels to < 1e-9 per pass (csrc/gate_tc.cuh, tools/tc_check.py).
  * Matrices with at most one non-zero per row and column (permutations, Pauli strings, diagonal phases) get no
- * compensation: permutations with entries in {0, +-1, +-i} are exact, diagonal phases lose < 1e-7 of the norm per
- * pass (measured 6e-8).  Measured against the reference CPU path:
+ * compensation: permutations with entries in {0, +-1, +-i} reproduce every amplitude to the 22 significant bits of
+ * the hi + lo split (exact on basis states and on amplitudes with <= 22 significant bits), diagonal phases lose
+ * < 1.5e-7 of the norm per pass (measured 6e-8).  Measured against the reference CPU path:
  * per-amplitude error 2e-8 on normalised states, 6e-11 on the amplitudes of circuit_q30; tuning "tc" = 0 keeps
  * everything on the FFMA2 kernels.
  *
@@ -292,6 +296,9 @@ typedef struct {
   double bytes_sent_per_shard;   /* sum over exchanges of shard_bytes * (1 - 2^-k) */
   double exchange_ms;            /* device time of the exchange kernels (CUDA events on the first local shard) */
   double barrier_wait_ms;        /* device time that shard spent in the barriers around them (skew between GPUs) */
+  uint64_t overlapped_swaps;     /* exchanges that ran chunk by chunk beside the last gate passes of their epoch ... */
+  uint64_t overlapped_gate_passes;   /* ... how many gate passes those were ... */
+  double overlap_ms;             /* ... and the device time of those pipelines (gates + exchange; not in exchange_ms) */
 } qb200_sv_stats;
 
 int qb200_sv_create(const int* devices, unsigned num_shards, unsigned num_qubits, int dtype, qb200_sv** sv);

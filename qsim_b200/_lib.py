@@ -87,7 +87,8 @@ class Gate(C.Structure):
 class SvStats(C.Structure):
     """qb200_sv_stats"""
     _fields_ = [("swaps", _u64), ("local_swap_passes", _u64), ("gate_passes", _u64),
-                ("bytes_sent_per_shard", _d), ("exchange_ms", _d), ("barrier_wait_ms", _d)]
+                ("bytes_sent_per_shard", _d), ("exchange_ms", _d), ("barrier_wait_ms", _d),
+                ("overlapped_swaps", _u64), ("overlapped_gate_passes", _u64), ("overlap_ms", _d)]
 
 
 SIGNATURES.update({
@@ -95,6 +96,7 @@ SIGNATURES.update({
     "qb200_state_alloc_on": (_i, [_vp, _u, _i, C.POINTER(_vp)]),
     "qb200_last_kernel_name": (C.c_char_p, [_vp]),
     "qb200_ctx_set_sm_limit": (_i, [_vp, _i]),
+    "qb200_ctx_set_occupancy_reduction": (_i, [_vp, _i]),
     "qb200_masked_norm": (_i, [_vp, _i, _vp, _u, _u64, _u64, _pd]),
     "qb200_collapse_scaled": (_i, [_vp, _i, _vp, _u, _u64, _u64, _d]),
     "qb200_sv_create": (_i, [C.POINTER(_i), _u, _u, _i, C.POINTER(_vp)]),

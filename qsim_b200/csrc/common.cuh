@@ -65,6 +65,8 @@ struct qb200_ctx {
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_limit = 0;               // > 0: persistent grids are sized for this many SMs (a concurrent exchange kernel owns the rest)
+  int occ_reduce = 0;             // persistent grids assume this many fewer resident CTAs per SM (an exchange kernel
+                                  // running beside the gates holds registers / threads / shared memory on every SM)
   const void* checked_ptr = nullptr;  // last state pointer verified to live on `device` (check_state_device)
   const char* last_kernel = "";   // name of the gate kernel the dispatcher picked last (qb200_last_kernel_name)
   qb200::Tuning tune;
@@ -101,6 +103,9 @@ int check_state_device(qb200_ctx* ctx, const void* p);
 int ensure_scratch(qb200_ctx* ctx, size_t bytes);
 int ensure_pinned(qb200_ctx* ctx, size_t bytes);
 int ensure_dmat(qb200_ctx* ctx);
+
+// resident CTAs per SM a persistent grid may count on
+inline int grid_occ(const qb200_ctx* ctx, int occ) { return occ - ctx->occ_reduce >= 1 ? occ - ctx->occ_reduce : 1; }
 
 // SMs a persistent grid may assume it owns.
 inline int grid_sms(const qb200_ctx* ctx) { return ctx->sm_limit > 0 && ctx->sm_limit < kNumSMs ? ctx->sm_limit : kNumSMs; }

@@ -312,6 +312,12 @@ int qb200_state_alloc_on(qb200_ctx* ctx, unsigned num_qubits, int dtype, void** 
 
 const char* qb200_last_kernel_name(const qb200_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
 
+int qb200_ctx_set_occupancy_reduction(qb200_ctx* ctx, int ctas_per_sm) {
+  if (!ctx || ctas_per_sm < 0) return QB200_ERR_INVALID;
+  ctx->occ_reduce = ctas_per_sm;
+  return QB200_OK;
+}
+
 int qb200_ctx_set_sm_limit(qb200_ctx* ctx, int sms) {
   if (!ctx || sms < 0) return QB200_ERR_INVALID;
   ctx->sm_limit = sms;

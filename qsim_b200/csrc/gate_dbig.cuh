@@ -107,7 +107,7 @@ int launch_dbig(qb200_ctx* ctx, double* st, const Geom& g, const double* m, doub
   int rc = stage_matrix(ctx, m, sizeof(double) * (size_t{2} << (2 * G)), &dmat);
   if (rc) return rc;
   const uint64_t need = (g.work + kDThreads - 1) / kDThreads;
-  uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
+  uint64_t persistent = uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ);
   if (EXPECT && persistent > kExpectMaxBlocks) persistent = kExpectMaxBlocks;
   const uint32_t blocks = (uint32_t) (need < persistent ? need : persistent);
   double* partials = nullptr;

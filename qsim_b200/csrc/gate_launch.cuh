@@ -66,7 +66,7 @@ int launch_pipe(qb200_ctx* ctx, float* st, const Geom& g, const MatParam<float, 
     return nb;
   });
   const uint64_t need = (g.work + PNT - 1) / PNT;
-  const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
+  const uint64_t persistent = uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ);
   const uint32_t blocks = (uint32_t) (need < persistent ? need : persistent);
   kern<<<blocks, PNT, smem, ctx->stream>>>(st, g, mat);
   QB_LAUNCHED(ctx);
@@ -91,7 +91,7 @@ int launch_tile(qb200_ctx* ctx, float* st, const TileGeom& t, const float* m) {
   });
   constexpr int warps = TNT / 32;
   const uint64_t need = (t.work + warps - 1) / warps;
-  const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
+  const uint64_t persistent = uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ);
   const uint32_t blocks = (uint32_t) (need < persistent ? need : persistent);
   kern<<<blocks, TNT, smem, ctx->stream>>>(st, t, mat);
   QB_LAUNCHED(ctx);
@@ -125,7 +125,7 @@ int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) 
         constexpr int kLoads = MODE == kV2T ? (1 << G) / 2 : (1 << G);  // per group
         constexpr int kUG = kLoads >= 4 ? 1 : 4 / kLoads;
         auto run = [&](auto kern, int occ, int ug, int contiguous) -> int {
-          const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
+          const uint64_t persistent = uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ);
           const uint64_t need = (blocks64 + ug - 1) / ug;
           const uint32_t nb = (uint32_t) (need < persistent ? need : persistent);
           int rc = ensure_scratch(ctx, (2 * size_t{nb} + 2) * sizeof(double));
@@ -165,7 +165,7 @@ int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) 
       if (ctx->tune.prefetch != 0) {
         auto kern = k_gate_reg<FP, G, MODE, UNROLL, false, true, NT, MINB, Mat>;
         static const int occ = resident_blocks(kern, NT);
-        const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
+        const uint64_t persistent = uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ);
         const uint32_t blocks = (uint32_t) (blocks64 < persistent ? blocks64 : persistent);
         kern<<<blocks, NT, 0, ctx->stream>>>(st, g, mat, nullptr);
         QB_LAUNCHED(ctx);

@@ -30,7 +30,7 @@ int launch_big_shape(qb200_ctx* ctx, float* st, const TileGeom& t, const float* 
     return nb;
   });
   const uint64_t need = (t.work + warps - 1) / warps;
-  uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
+  uint64_t persistent = uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ);
   if (EXPECT && persistent > kExpectMaxBlocks) persistent = kExpectMaxBlocks;
   const uint32_t blocks = (uint32_t) (need < persistent ? need : persistent);
 

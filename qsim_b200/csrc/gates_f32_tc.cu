@@ -50,7 +50,7 @@ int launch_tc_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
   MatParam<float, G> mat;
   mat.fill(m);
   const uint64_t tiles = g.work >> 7;
-  const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
+  const uint64_t persistent = uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ);
   const uint32_t blocks = (uint32_t) (tiles < persistent ? tiles : persistent);
   kern<<<blocks, kTcThreads, smem, ctx->stream>>>(st, g, mat);
   QB_LAUNCHED(ctx);
@@ -77,7 +77,7 @@ int launch_tca_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m) {
   MatParam<float, G> mat;
   mat.fill(m);
   const uint64_t tiles = g.work >> 7 >> (MT - 1);
-  const uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
+  const uint64_t persistent = uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ);
   const uint32_t blocks = (uint32_t) (tiles < persistent ? tiles : persistent);
   kern<<<blocks, kTcThreads * MT, smem, ctx->stream>>>(st, g, mat);
   QB_LAUNCHED(ctx);
@@ -109,7 +109,7 @@ int launch_tcx_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m, d
     return nb;
   });
   const uint64_t tiles = g.work >> 7;
-  uint64_t persistent = uint64_t(grid_sms(ctx)) * occ;
+  uint64_t persistent = uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ);
   if (EXPECT && persistent > kExpectMaxBlocks) persistent = kExpectMaxBlocks;
   const uint32_t blocks = (uint32_t) (tiles < persistent ? tiles : persistent);
   double* partials = nullptr;

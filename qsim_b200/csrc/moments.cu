@@ -227,7 +227,7 @@ int one_qubit_moments(qb200_ctx* ctx, const FP* st, unsigned n, double* out) {
     return nb;
   });
   const uint64_t ntiles = uint64_t{1} << (n - T);
-  const uint32_t blocks = (uint32_t) std::min<uint64_t>(ntiles, uint64_t(grid_sms(ctx)) * occ);
+  const uint32_t blocks = (uint32_t) std::min<uint64_t>(ntiles, uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ));
   const size_t pdoubles = size_t{blocks} * kMomMaxT * 4;
   int rc = ensure_scratch(ctx, (pdoubles + 4 * size_t{n}) * sizeof(double));
   if (rc) return rc;

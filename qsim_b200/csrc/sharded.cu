@@ -29,6 +29,12 @@
 
 namespace qb200 {
 
+// gates_f{32,64}_apply.cu: the dispatcher behind qb200_apply_controlled_gate (no limit on targets under control)
+int gate_apply_f32(qb200_ctx* ctx, float* st, unsigned n, const unsigned* qs, unsigned nq, const unsigned* cqs,
+                   unsigned nc, uint64_t cvals, const float* m, double* out);
+int gate_apply_f64(qb200_ctx* ctx, double* st, unsigned n, const unsigned* qs, unsigned nq, const unsigned* cqs,
+                   unsigned nc, uint64_t cvals, const double* m, double* out);
+
 constexpr unsigned kMaxGlobal = 5;        // up to 32 shards
 constexpr unsigned kMaxShards = 1u << kMaxGlobal;
 constexpr unsigned kMinInplaceBit = 4;    // in-place exchange: victims below this bit are lifted first (short runs)
@@ -53,9 +59,22 @@ constexpr int kRemapThreads = 256;
 struct RemapGeom {
   void* dst[kMaxShards];   // new buffer of the shard whose exchanged rank bits equal v
   uint64_t tiles;          // 2^(nl - T)
+  uint64_t walk;           // tile counters this launch walks: tiles >> nchunk
   uint32_t k, kl, my, nl, T;
+  // a launch may cover one CHUNK of the shard only (exchange overlapped with gates, run_overlapped): nchunk bits of
+  // the tile counter are pinned to cval, at positions cpos[] (ascending, in the counter with those bits present)
+  uint32_t nchunk, cval, cpos[3];
   uint32_t lbits[kMaxGlobal];  // ascending; the first kl are below T
 };
+
+// dense counter inside a chunk -> tile counter (identity when the launch covers the whole shard)
+__device__ __forceinline__ uint64_t chunk_counter(uint64_t cc, const RemapGeom& g) {
+  for (uint32_t j = 0; j < g.nchunk; ++j) {
+    const uint64_t lo = cc & ((uint64_t{1} << g.cpos[j]) - 1);
+    cc = (((cc >> g.cpos[j]) << 1 | ((g.cval >> j) & 1u)) << g.cpos[j]) | lo;
+  }
+  return cc;
+}
 
 // FP = float: 16-byte items hold two amplitudes; FP = double: one.
 template <typename FP>
@@ -70,7 +89,8 @@ k_remap_push(const FP* __restrict__ src, const __grid_constant__ RemapGeom g) {
   const uint32_t kh = g.k - g.kl;
   const uint32_t sub_bits = g.T - g.kl;                      // log2(amplitudes per destination run)
   const uint32_t my_high = g.my >> g.kl;
-  for (uint64_t c = blockIdx.x; c < g.tiles; c += gridDim.x) {
+  for (uint64_t cc = blockIdx.x; cc < g.walk; cc += gridDim.x) {
+    const uint64_t c = chunk_counter(cc, g);
     // tile counter -> tile index: the kh victim bits above the tile vary fastest, XOR-ed with this shard's value
     const uint32_t v_high = ((uint32_t) c & ((1u << kh) - 1)) ^ my_high;
     uint64_t tau = c >> kh;                                  // bits of the tile index outside the victims
@@ -156,8 +176,10 @@ __device__ __forceinline__ void wait_all() { asm volatile("cp.async.bulk.wait_gr
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 }  // namespace bulk
 
-template <typename FP>
-__global__ void __launch_bounds__(kRemapThreads)
+// NT threads: 256 when the exchange runs alone; 64 when gate kernels run beside it (the threads only do the
+// shared->shared scatter; 64 x 31 registers fit next to three resident k_gate_tca<4> CTAs of 256 x 80).
+template <typename FP, int NT>
+__global__ void __launch_bounds__(NT)
 k_remap_push_tma(const FP* __restrict__ src, const __grid_constant__ RemapGeom g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[2];
@@ -190,20 +212,21 @@ k_remap_push_tma(const FP* __restrict__ src, const __grid_constant__ RemapGeom g
     return tau;
   };
 
-  uint64_t c = blockIdx.x;
-  if (threadIdx.x == 0 && c < g.tiles) {
+  uint64_t cc = blockIdx.x;
+  if (threadIdx.x == 0 && cc < g.walk) {
     uint32_t vh;
-    const uint64_t tau = tile_index(c, &vh);
+    const uint64_t tau = tile_index(chunk_counter(cc, g), &vh);
     bulk::mbar_expect_tx(full_s, tile_bytes);
     bulk::load(in_s, reinterpret_cast<const unsigned char*>(src) + tau * tile_bytes, tile_bytes, full_s);
   }
-  for (uint32_t it = 0; c < g.tiles; c += gridDim.x, ++it) {
+  for (uint32_t it = 0; cc < g.walk; cc += gridDim.x, ++it) {
     const uint32_t s = it & 1;
+    const uint64_t c = chunk_counter(cc, g);
     if (threadIdx.x == 0) {
-      const uint64_t cn = c + gridDim.x;
-      if (cn < g.tiles) {  // input stage s^1 was consumed by the scatter of the previous iteration
+      const uint64_t cn = cc + gridDim.x;
+      if (cn < g.walk) {  // input stage s^1 was consumed by the scatter of the previous iteration
         uint32_t vh;
-        const uint64_t tau = tile_index(cn, &vh);
+        const uint64_t tau = tile_index(chunk_counter(cn, g), &vh);
         bulk::mbar_expect_tx(full_s + 8 * (s ^ 1), tile_bytes);
         bulk::load(in_s + (s ^ 1) * tile_bytes, reinterpret_cast<const unsigned char*>(src) + tau * tile_bytes, tile_bytes,
                    full_s + 8 * (s ^ 1));
@@ -214,7 +237,7 @@ k_remap_push_tma(const FP* __restrict__ src, const __grid_constant__ RemapGeom g
     bulk::mbar_wait(full_s + 8 * s, (it >> 1) & 1);
     const unsigned char* const tin = in_p + s * tile_bytes;
     unsigned char* const tout = out_p + s * tile_bytes;
-    for (uint32_t i0 = threadIdx.x; i0 < items; i0 += kRemapThreads) {
+    for (uint32_t i0 = threadIdx.x; i0 < items; i0 += NT) {
       const uint4 x = reinterpret_cast<const uint4*>(tin)[i0];
 #pragma unroll
       for (int a = 0; a < APT; ++a) {
@@ -303,6 +326,8 @@ struct Shard {
   void* buf[2] = {nullptr, nullptr};
   uint32_t* flags = nullptr;
   cudaEvent_t ev = nullptr;
+  cudaStream_t stream2 = nullptr;   // gates that run beside an exchange (overlap)
+  cudaEvent_t ev_chunk = nullptr, ev_join = nullptr;
 };
 
 struct SvStats {
@@ -310,6 +335,9 @@ struct SvStats {
   double bytes_sent_per_shard = 0;   // summed over swaps
   double exchange_ms = 0;            // device time of the exchange kernels (events on the first local shard's stream)
   double wait_ms = 0;                // device time the first local shard spent in the barriers around them (rank skew)
+  uint64_t overlapped_swaps = 0;     // exchanges that ran chunk by chunk beside the last gates of their epoch
+  uint64_t overlapped_gate_passes = 0;   // ... and how many gate passes those were
+  double overlap_ms = 0;             // device time of those pipelines (gates + exchange), not part of exchange_ms
 };
 
 }  // namespace qb200
@@ -339,10 +367,16 @@ struct qb200_sv {
   int reorder = 1;
   int push_kernel = 1;                   // 1: bulk-copy engine (k_remap_push_tma, default); 0: st.global from registers
   int push_ctas_per_sm = 0;              // 0 = default of the chosen kernel
+  int overlap_ctas_per_sm = 0;           // CTAs per SM of the slim push kernel that runs beside gates (0 = 1)
+  int overlap = 1;                       // qb200_sv_run: the last gates of an epoch run beside its exchange, chunk by chunk
+  int overlap_chunks_log2 = 2;           // 2^this chunks per shard
+  int overlap_max_gates = 6;             // gate passes pipelined against one exchange (enough to cover it, see run_overlapped)
+  int overlap_occ_reduce = 0;            // resident gate CTAs per SM given up while the slim push kernel runs beside them
   SvStats stats;
   std::vector<uint64_t> plan_key;        // gate structure + global set the cached schedule was made for
   std::vector<int64_t> plan_steps;
   std::vector<std::array<cudaEvent_t, 4>> ev_quads;  // exchange timing, first local shard (timing_mark)
+  std::vector<char> ev_overlapped;       // quad i timed an overlapped exchange (its [1]..[2] stretch includes gates)
   size_t ev_used = 0;
   int last_error = 0;
 };
@@ -461,6 +495,9 @@ static int make_shard(qb200_sv* sv, int device, unsigned rank) {
   SV_CUDA(sv, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   qb200_ctx_set_stream(s.ctx, s.stream);
   SV_CUDA(sv, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  SV_CUDA(sv, cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
+  SV_CUDA(sv, cudaEventCreateWithFlags(&s.ev_chunk, cudaEventDisableTiming));
+  SV_CUDA(sv, cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
   int rc = qb200_state_alloc_on(s.ctx, sv->nl, sv->dtype, &s.buf[0]);
   if (rc) { sv->sh.push_back(s); return rc; }
   SV_CUDA(sv, cudaMalloc((void**) &s.flags, 256 * sizeof(uint32_t)));
@@ -565,8 +602,11 @@ static void permute_matrix(const FP* m, unsigned nq, const unsigned* order, std:
 
 // Applies a gate (expect = false) or evaluates an operator (expect = true, result summed over the local shards
 // into out[2]) whose TARGETS are all local.  Controls may be global: they select the shards that take part.
+// chunk_bits / chunk_val (gates only): the pass is restricted to the part of every shard whose PHYSICAL local bits
+// chunk_bits[] carry chunk_val -- extra controls of the kernel, none of them a target or control of the gate.
 static int local_gate(qb200_sv* sv, const unsigned* qs, unsigned nq, const unsigned* cqs, unsigned nc,
-                      uint64_t cvals, const void* matrix, bool expect, double* out) {
+                      uint64_t cvals, const void* matrix, bool expect, double* out,
+                      const unsigned* chunk_bits = nullptr, unsigned nchunk = 0, unsigned chunk_val = 0) {
   if (nq > kMaxTargets) return QB200_ERR_UNSUPPORTED;
   if (nc > 0 && nq > kMaxCtrlTargets) return QB200_ERR_UNSUPPORTED;
   unsigned phys[kMaxTargets], order[kMaxTargets], sorted[kMaxTargets];
@@ -612,6 +652,7 @@ static int local_gate(qb200_sv* sv, const unsigned* qs, unsigned nq, const unsig
       lctl.emplace_back(p, cv.second);
     }
   }
+  for (unsigned j = 0; j < nchunk; ++j) lctl.emplace_back(chunk_bits[j], (chunk_val >> j) & 1u);
   std::sort(lctl.begin(), lctl.end());
   unsigned lc[64];
   uint64_t lcv = 0;
@@ -628,6 +669,11 @@ static int local_gate(qb200_sv* sv, const unsigned* qs, unsigned nq, const unsig
     if (expect) {
       double dummy[2];
       rc = qb200_expectation_value(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, sorted, nq, m, dummy);
+    } else if (nchunk) {
+      // the chunk bits are kernel-level controls: the reference's "at most 4 targets under control" does not apply
+      rc = sv->dtype == QB200_F32
+          ? gate_apply_f32(s.ctx, (float*) cur_buf(sv, s), sv->nl, sorted, nq, lc, (unsigned) lctl.size(), lcv, (const float*) m, nullptr)
+          : gate_apply_f64(s.ctx, (double*) cur_buf(sv, s), sv->nl, sorted, nq, lc, (unsigned) lctl.size(), lcv, (const double*) m, nullptr);
     } else {
       rc = qb200_apply_controlled_gate(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, sorted, nq, lc,
                                        (unsigned) lctl.size(), lcv, m);
@@ -643,7 +689,7 @@ static int local_gate(qb200_sv* sv, const unsigned* qs, unsigned nq, const unsig
       if (rc2 && !rc) rc = rc2;
       if (cnt) { out[0] += r[0]; out[1] += r[1]; }
     }
-  } else {
+  } else if (!nchunk || chunk_val == 0) {
     ++sv->stats.gate_passes;
   }
   return rc;
@@ -687,7 +733,9 @@ static void timing_mark(qb200_sv* sv, int which) {
     std::array<cudaEvent_t, 4> q{};
     for (auto& e : q) cudaEventCreate(&e);
     sv->ev_quads.push_back(q);
+    sv->ev_overlapped.push_back(0);
   }
+  if (which == 0) sv->ev_overlapped[sv->ev_used] = 0;
   cudaEventRecord(sv->ev_quads[sv->ev_used][which], sv->sh[0].stream);
   if (which == 3) ++sv->ev_used;
 }
@@ -698,7 +746,8 @@ static int timing_collect(qb200_sv* sv) {
     float pre = 0, run = 0, post = 0;
     if (cudaEventElapsedTime(&pre, q[0], q[1]) == cudaSuccess && cudaEventElapsedTime(&run, q[1], q[2]) == cudaSuccess &&
         cudaEventElapsedTime(&post, q[2], q[3]) == cudaSuccess) {
-      sv->stats.exchange_ms += run;
+      if (sv->ev_overlapped[i]) sv->stats.overlap_ms += run;
+      else sv->stats.exchange_ms += run;
       sv->stats.wait_ms += pre + post;
     } else {
       (void) cudaGetLastError();
@@ -708,12 +757,117 @@ static int timing_collect(qb200_sv* sv) {
   return QB200_OK;
 }
 
-// victims (logical, local) <-> incoming (logical, global); k <= g.
-static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* incoming_in, unsigned k) {
-  if (k == 0) return QB200_OK;
+// ---- out-of-place exchange in three steps: prepare (geometry + spare buffers), launch per shard, finish (map) ----
+struct PushPlan {
+  RemapGeom rg{};                        // my / dst are filled per shard at launch
+  std::vector<unsigned> victims, incoming;   // logical qubits, pairs ordered by the victims' physical bits
+  unsigned gb[kMaxGlobal] = {};          // rank bit victim j goes to
+  unsigned k = 0;
+  size_t smem = 0;                       // bytes of one tile
+};
+
+// QB200_ERR_UNSUPPORTED: this exchange cannot go out of place (tiny shard or no room for the spare buffers)
+static int push_prepare(qb200_sv* sv, const std::vector<unsigned>& victims, const std::vector<unsigned>& incoming,
+                        PushPlan* pp) {
+  const unsigned k = (unsigned) victims.size();
+  if (sv->swap_mode == 0) return QB200_ERR_UNSUPPORTED;
+  // the push kernel sorts tiles of 2^T amplitudes by the victim bits they contain: every destination run must
+  // hold at least one 16-byte item (a shard of a handful of qubits with all of them victims does not qualify)
+  const unsigned T = std::min<unsigned>(kTileBits, sv->nl);
+  unsigned kl = 0;
+  for (unsigned j = 0; j < k; ++j) kl += sv->pos[victims[j]] < T;
+  if (T < kl + (sv->dtype == QB200_F32 ? 1u : 0u)) return sv->swap_mode == 1 ? QB200_ERR_INVALID : QB200_ERR_UNSUPPORTED;
+  if (ensure_alt(sv) != QB200_OK) return sv->swap_mode == 1 ? QB200_ERR_OOM : QB200_ERR_UNSUPPORTED;
+  pp->victims = victims;
+  pp->incoming = incoming;
+  pp->k = k;
+  RemapGeom& rg = pp->rg;
+  rg = RemapGeom{};
+  rg.k = k;
+  rg.nl = sv->nl;
+  rg.T = T;   // tiles of 2^T amplitudes; tiny shards shrink the tile
+  rg.kl = kl;
+  for (unsigned j = 0; j < k; ++j) {
+    rg.lbits[j] = sv->pos[victims[j]];
+    pp->gb[j] = sv->pos[incoming[j]] - sv->nl;
+  }
+  rg.tiles = uint64_t{1} << (sv->nl - rg.T);
+  rg.walk = rg.tiles;
+  pp->smem = (size_t{1} << rg.T) * 2 * scalar_size(sv->dtype);
+  return QB200_OK;
+}
+
+template <typename FP, int NT>
+static void launch_push_tma(qb200_sv* sv, Shard& s, const RemapGeom& rg, size_t smem4, int ctas_per_sm, cudaStream_t stream) {
+  static PerDevice attr;
+  attr.get(s.ctx, [&] {
+    cudaFuncSetAttribute(k_remap_push_tma<FP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (4 * 16384 * sizeof(FP) / 4));
+    return 1;
+  });
+  const uint64_t b2 = std::min<uint64_t>(rg.walk, uint64_t{kNumSMs} * ctas_per_sm);
+  k_remap_push_tma<FP, NT><<<(uint32_t) b2, NT, smem4, stream>>>((const FP*) s.buf[sv->cur], rg);
+}
+
+// one shard's push (the whole shard, or the chunk pp.rg describes) on `stream`; slim = the 64-thread variant that
+// fits beside resident gate kernels
+static int push_launch(qb200_sv* sv, Shard& s, PushPlan& pp, cudaStream_t stream, bool slim) {
+  DevScope d(s.device);
+  RemapGeom& rg = pp.rg;
+  const int nb = 1 - sv->cur;
+  rg.my = pick_bits(s.rank, pp.gb, pp.k);
+  for (unsigned v = 0; v < (1u << pp.k); ++v) rg.dst[v] = sv->peer_buf[nb][with_bits(s.rank, pp.gb, pp.k, v)];
+  if (sv->push_kernel == 1) {
+    // bulk-copy variant: 2 + 2 stages of one tile each
+    const size_t smem4 = 4 * pp.smem;
+    const bool f32 = sv->dtype == QB200_F32;
+    if (slim) {
+      const int per_sm = sv->overlap_ctas_per_sm > 0 ? sv->overlap_ctas_per_sm : 1;
+      if (f32) launch_push_tma<float, 64>(sv, s, rg, smem4, per_sm, stream);
+      else launch_push_tma<double, 64>(sv, s, rg, smem4, per_sm, stream);
+    } else {
+      const int per_sm = sv->push_ctas_per_sm > 0 ? sv->push_ctas_per_sm : (f32 ? 3 : 1);
+      if (f32) launch_push_tma<float, kRemapThreads>(sv, s, rg, smem4, per_sm, stream);
+      else launch_push_tma<double, kRemapThreads>(sv, s, rg, smem4, per_sm, stream);
+    }
+  } else {
+    const uint64_t blocks = std::min<uint64_t>(rg.walk, uint64_t{kNumSMs} * 6);
+    if (sv->dtype == QB200_F32)
+      k_remap_push<float><<<(uint32_t) blocks, kRemapThreads, pp.smem, stream>>>((const float*) s.buf[sv->cur], rg);
+    else
+      k_remap_push<double><<<(uint32_t) blocks, kRemapThreads, pp.smem, stream>>>((const double*) s.buf[sv->cur], rg);
+  }
+  ++s.ctx->launches;
+  SV_CUDA(sv, cudaPeekAtLastError());
+  return QB200_OK;
+}
+
+// after the trailing barrier: the spare buffers hold the state; new qubit map
+static void push_finish(qb200_sv* sv, const PushPlan& pp) {
+  sv->cur = 1 - sv->cur;
+  // the remaining local qubits keep their order in the low bits, incoming j sits at nl - k + j
+  const unsigned k = pp.k;
+  std::vector<unsigned> vb(pp.rg.lbits, pp.rg.lbits + k);
+  for (unsigned q = 0; q < sv->n; ++q) {
+    const unsigned p = sv->pos[q];
+    if (p >= sv->nl) continue;
+    if (std::find(pp.victims.begin(), pp.victims.end(), q) != pp.victims.end()) continue;
+    unsigned below = 0;
+    for (unsigned b : vb) below += b < p;
+    sv->pos[q] = p - below;
+  }
+  for (unsigned j = 0; j < k; ++j) {
+    sv->pos[pp.victims[j]] = sv->nl + pp.gb[j];
+    sv->pos[pp.incoming[j]] = sv->nl - k + j;
+  }
+  ++sv->stats.swaps;
+  sv->stats.bytes_sent_per_shard += (double) shard_bytes(sv) * (1.0 - 1.0 / (double) (1u << k));
+}
+
+// validates an exchange and orders its (victim, incoming) pairs by the victims' physical bits (the kernels want
+// those ascending); victim j goes to the rank bit incoming j leaves
+static int order_pairs(qb200_sv* sv, const unsigned* victims_in, const unsigned* incoming_in, unsigned k,
+                       std::vector<unsigned>* victims, std::vector<unsigned>* incoming) {
   if (k > sv->g) return QB200_ERR_INVALID;
-  // victim j goes to the rank bit incoming j leaves: keep the caller's pairing, order the pairs by the victims'
-  // physical bits (the kernels want those ascending)
   for (unsigned j = 0; j < k; ++j) {
     if (victims_in[j] >= sv->n || incoming_in[j] >= sv->n) return QB200_ERR_INVALID;
     if (sv->pos[victims_in[j]] >= sv->nl || sv->pos[incoming_in[j]] < sv->nl) return QB200_ERR_INVALID;
@@ -721,98 +875,36 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
   std::vector<unsigned> perm(k);
   for (unsigned j = 0; j < k; ++j) perm[j] = j;
   std::sort(perm.begin(), perm.end(), [&](unsigned a, unsigned b) { return sv->pos[victims_in[a]] < sv->pos[victims_in[b]]; });
-  std::vector<unsigned> victims(k), incoming(k);
-  unsigned gb[kMaxGlobal];
+  victims->resize(k);
+  incoming->resize(k);
   for (unsigned j = 0; j < k; ++j) {
-    victims[j] = victims_in[perm[j]];
-    incoming[j] = incoming_in[perm[j]];
-    gb[j] = sv->pos[incoming[j]] - sv->nl;
+    (*victims)[j] = victims_in[perm[j]];
+    (*incoming)[j] = incoming_in[perm[j]];
   }
-  bool out_of_place = sv->swap_mode != 0;
-  {
-    // the push kernel sorts tiles of 2^T amplitudes by the victim bits they contain: every destination run must
-    // hold at least one 16-byte item (a shard of a handful of qubits with all of them victims does not qualify)
-    const unsigned T = std::min<unsigned>(kTileBits, sv->nl);
-    unsigned kl = 0;
-    for (unsigned j = 0; j < k; ++j) kl += sv->pos[victims[j]] < T;
-    if (T < kl + (sv->dtype == QB200_F32 ? 1u : 0u)) {
-      if (sv->swap_mode == 1) return QB200_ERR_INVALID;
-      out_of_place = false;
-    }
-  }
-  if (out_of_place && ensure_alt(sv) != QB200_OK) {
-    if (sv->swap_mode == 1) return QB200_ERR_OOM;
-    out_of_place = false;
-  }
+  return QB200_OK;
+}
+
+// victims (logical, local) <-> incoming (logical, global); k <= g.
+static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* incoming_in, unsigned k) {
+  if (k == 0) return QB200_OK;
+  std::vector<unsigned> victims, incoming;
+  SV_TRY(order_pairs(sv, victims_in, incoming_in, k, &victims, &incoming));
+  unsigned gb[kMaxGlobal];
+  for (unsigned j = 0; j < k; ++j) gb[j] = sv->pos[incoming[j]] - sv->nl;
+  PushPlan pp;
+  const int prc = push_prepare(sv, victims, incoming, &pp);
+  if (prc != QB200_OK && prc != QB200_ERR_UNSUPPORTED) return prc;
   const double sent = (double) shard_bytes(sv) * (1.0 - 1.0 / (double) (1u << k));
 
-  if (out_of_place) {
-    RemapGeom rg{};
-    rg.k = k;
-    rg.nl = sv->nl;
-    // tiles of 2^T amplitudes; tiny shards shrink the tile (at least one 16-byte item per destination run)
-    rg.T = std::min<unsigned>(kTileBits, sv->nl);
-    rg.kl = 0;
-    for (unsigned j = 0; j < k; ++j) {
-      rg.lbits[j] = sv->pos[victims[j]];
-      if (rg.lbits[j] < rg.T) ++rg.kl;
-    }
-    rg.tiles = uint64_t{1} << (sv->nl - rg.T);
-    const size_t smem = (size_t{1} << rg.T) * 2 * scalar_size(sv->dtype);
-    const int nb = 1 - sv->cur;
+  if (prc == QB200_OK) {
     timing_mark(sv, 0);
     timing_mark(sv, 1);  // no leading barrier: the spare buffers are free (see ensure_alt)
-    for (auto& s : sv->sh) {
-      DevScope d(s.device);
-      rg.my = pick_bits(s.rank, gb, k);
-      for (unsigned v = 0; v < (1u << k); ++v) rg.dst[v] = sv->peer_buf[nb][with_bits(s.rank, gb, k, v)];
-      uint64_t blocks = rg.tiles;
-      const uint64_t cap = uint64_t{kNumSMs} * 6;
-      if (blocks > cap) blocks = cap;
-      if (sv->push_kernel == 1) {
-        // bulk-copy variant: 2 + 2 stages of one tile each; opt in to the shared memory once per device
-        const size_t smem4 = 4 * smem;
-        static PerDevice attr_f, attr_d;
-        if (sv->dtype == QB200_F32) {
-          attr_f.get(s.ctx, [&] {
-            cudaFuncSetAttribute(k_remap_push_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16384);
-            return 1;
-          });
-          uint64_t b2 = std::min<uint64_t>(rg.tiles, uint64_t{kNumSMs} * (sv->push_ctas_per_sm > 0 ? sv->push_ctas_per_sm : 3));
-          k_remap_push_tma<float><<<(uint32_t) b2, kRemapThreads, smem4, s.stream>>>((const float*) s.buf[sv->cur], rg);
-        } else {
-          attr_d.get(s.ctx, [&] {
-            cudaFuncSetAttribute(k_remap_push_tma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768);
-            return 1;
-          });
-          uint64_t b2 = std::min<uint64_t>(rg.tiles, uint64_t{kNumSMs} * (sv->push_ctas_per_sm > 0 ? sv->push_ctas_per_sm : 1));
-          k_remap_push_tma<double><<<(uint32_t) b2, kRemapThreads, smem4, s.stream>>>((const double*) s.buf[sv->cur], rg);
-        }
-      } else if (sv->dtype == QB200_F32)
-        k_remap_push<float><<<(uint32_t) blocks, kRemapThreads, smem, s.stream>>>((const float*) s.buf[sv->cur], rg);
-      else
-        k_remap_push<double><<<(uint32_t) blocks, kRemapThreads, smem, s.stream>>>((const double*) s.buf[sv->cur], rg);
-      ++s.ctx->launches;
-      SV_CUDA(sv, cudaPeekAtLastError());
-    }
+    for (auto& s : sv->sh) SV_TRY(push_launch(sv, s, pp, s.stream, false));
     timing_mark(sv, 2);  // (recorded after the launches of every local shard; the first shard's stream only holds its own)
     SV_TRY(barrier(sv));
     timing_mark(sv, 3);
-    sv->cur = nb;
-    // new map: the remaining local qubits keep their order in the low bits, incoming j sits at nl - k + j
-    std::vector<unsigned> vb(rg.lbits, rg.lbits + k);
-    for (unsigned q = 0; q < sv->n; ++q) {
-      const unsigned p = sv->pos[q];
-      if (p >= sv->nl) continue;
-      if (std::find(victims.begin(), victims.end(), q) != victims.end()) continue;
-      unsigned below = 0;
-      for (unsigned b : vb) below += b < p;
-      sv->pos[q] = p - below;
-    }
-    for (unsigned j = 0; j < k; ++j) {
-      sv->pos[victims[j]] = sv->nl + gb[j];
-      sv->pos[incoming[j]] = sv->nl - k + j;
-    }
+    push_finish(sv, pp);
+    return QB200_OK;
   } else {
     // in place (k_p2p_swap): local bit <-> rank bit; low victims are lifted first, at most 3 bits per pass
     for (unsigned off = 0; off < k; off += 3) {
@@ -856,6 +948,124 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
   }
   ++sv->stats.swaps;
   sv->stats.bytes_sent_per_shard += sent;
+  return QB200_OK;
+}
+
+// ---- exchange overlapped with the last gates of its epoch ------------------------------------------------------
+// The push is out of place, so a part of the shard can leave as soon as the last gate has passed over it.  The
+// shard is cut into 2^c CHUNKS by c physical local bits that are neither victims nor touched by the last L gates of
+// the epoch; chunk by chunk those L gates run as passes with the chunk bits as extra controls (main stream), and the
+// chunk's push follows on a second stream -- while the gates are already on the next chunk.  A gate pass streams
+// the chunk from HBM (2 x 16 B per amplitude at ~6 TB/s), the push moves (1 - 2^-k) of it at ~0.7 TB/s over NVLink:
+// L >= 4.3 (1 - 2^-k) passes cover the exchange, so L is capped at overlap_max_gates.  Exposed: the gates of the
+// first chunk and the push of the last one.  No extra synchronisation between GPUs: the destinations are the spare
+// buffers, idle until the trailing barrier.
+static void touch(qb200_sv* sv, const unsigned* qs, unsigned nq);
+
+struct OverlapSpec {
+  bool valid = false;
+  uint64_t start = 0, swap = 0;         // steps[start .. swap) are the pipelined gates, steps[swap] the exchange
+  unsigned nchunk = 0, chunk_bits[3] = {};
+  std::vector<unsigned> victims, incoming;
+};
+
+static void plan_overlap(qb200_sv* sv, const qb200_gate* gates, const std::vector<int64_t>& steps, uint64_t from,
+                         OverlapSpec* spec) {
+  spec->valid = false;
+  if (!sv->overlap || sv->swap_mode == 0 || sv->alt_failed || sv->P == 1) return;
+  uint64_t ws = from;
+  while (ws < steps.size() && steps[ws] >= 0) ++ws;
+  if (ws >= steps.size() || ws == from) return;
+  const unsigned k = (unsigned) -steps[ws];
+  unsigned vq[kMaxGlobal], iq[kMaxGlobal];
+  for (unsigned j = 0; j < k; ++j) vq[j] = (unsigned) steps[ws + 1 + j];
+  for (unsigned j = 0; j < k; ++j) iq[j] = (unsigned) steps[ws + 1 + k + j];
+  if (order_pairs(sv, vq, iq, k, &spec->victims, &spec->incoming) != QB200_OK) return;
+  const unsigned T = std::min<unsigned>(kTileBits, sv->nl);
+  const unsigned c = (unsigned) std::min(3, std::max(1, sv->overlap_chunks_log2));
+  uint64_t free_bits = 0;
+  for (unsigned p = T; p < sv->nl; ++p) free_bits |= uint64_t{1} << p;
+  for (unsigned q : spec->victims) free_bits &= ~(uint64_t{1} << sv->pos[q]);
+  if ((unsigned) __builtin_popcountll(free_bits) < c) return;
+  unsigned L = 0;
+  for (uint64_t i = ws; i-- > from && (int) L < sv->overlap_max_gates;) {
+    const qb200_gate& gt = gates[steps[i]];
+    if (gt.num_targets > 5 || (gt.num_targets == 5 && sv->dtype != QB200_F32)) break;
+    uint64_t touched = 0;
+    bool ok = true;
+    for (unsigned j = 0; j < gt.num_targets; ++j) {
+      const unsigned p = sv->pos[gt.qs[j]];
+      if (p >= sv->nl) { ok = false; break; }   // (cannot happen in a planned epoch)
+      touched |= uint64_t{1} << p;
+    }
+    for (unsigned j = 0; j < gt.num_controls && ok; ++j) {
+      const unsigned p = sv->pos[gt.cqs[j]];
+      if (p < sv->nl) touched |= uint64_t{1} << p;
+    }
+    if (!ok || (unsigned) __builtin_popcountll(free_bits & ~touched) < c) break;
+    free_bits &= ~touched;
+    ++L;
+  }
+  if (L == 0) return;
+  for (unsigned j = c; j-- > 0;) {               // the highest free bits: the longest contiguous runs
+    const unsigned p = 63 - (unsigned) __builtin_clzll(free_bits);
+    spec->chunk_bits[j] = p;
+    free_bits &= ~(uint64_t{1} << p);
+  }
+  spec->nchunk = c;
+  spec->swap = ws;
+  spec->start = ws - L;
+  spec->valid = true;
+}
+
+static int run_overlapped(qb200_sv* sv, const qb200_gate* gates, const std::vector<int64_t>& steps, const OverlapSpec& spec,
+                          PushPlan& pp) {
+  RemapGeom& rg = pp.rg;
+  const unsigned c = spec.nchunk, kh = rg.k - rg.kl;
+  rg.nchunk = c;
+  for (unsigned j = 0; j < c; ++j) {
+    unsigned below = 0;
+    for (unsigned i = rg.kl; i < rg.k; ++i) below += rg.lbits[i] < spec.chunk_bits[j];
+    rg.cpos[j] = kh + (spec.chunk_bits[j] - rg.T) - below;   // position in the tile counter: [packed tile bits | kh victim bits]
+  }
+  rg.walk = rg.tiles >> c;
+  timing_mark(sv, 0);
+  timing_mark(sv, 1);
+  sv->ev_overlapped[sv->ev_used] = 1;
+  for (auto& s : sv->sh) s.ctx->occ_reduce = sv->overlap_occ_reduce;
+  int rc = QB200_OK;
+  for (unsigned v = 0; v < (1u << c) && rc == QB200_OK; ++v) {
+    for (uint64_t i = spec.start; i < spec.swap && rc == QB200_OK; ++i) {
+      const qb200_gate& gt = gates[steps[i]];
+      if (v == 0) touch(sv, gt.qs, gt.num_targets);
+      rc = local_gate(sv, gt.qs, gt.num_targets, gt.cqs, gt.num_controls, gt.cvals, gt.matrix, false, nullptr,
+                      spec.chunk_bits, c, v);
+    }
+    rg.cval = v;
+    for (auto& s : sv->sh) {
+      if (rc != QB200_OK) break;
+      DevScope d(s.device);
+      if (cudaEventRecord(s.ev_chunk, s.stream) != cudaSuccess || cudaStreamWaitEvent(s.stream2, s.ev_chunk, 0) != cudaSuccess) {
+        (void) cudaGetLastError();
+        rc = QB200_ERR_CUDA;
+        break;
+      }
+      rc = push_launch(sv, s, pp, s.stream2, true);
+    }
+  }
+  for (auto& s : sv->sh) {
+    s.ctx->occ_reduce = 0;
+    DevScope d(s.device);
+    cudaEventRecord(s.ev_join, s.stream2);
+    cudaStreamWaitEvent(s.stream, s.ev_join, 0);
+  }
+  if (rc != QB200_OK) return rc;
+  timing_mark(sv, 2);
+  SV_TRY(barrier(sv));
+  timing_mark(sv, 3);
+  push_finish(sv, pp);
+  ++sv->stats.overlapped_swaps;
+  sv->stats.overlapped_gate_passes += spec.swap - spec.start;
   return QB200_OK;
 }
 
@@ -1006,6 +1216,9 @@ int qb200_sv_destroy(qb200_sv* sv) {
     if (s.buf[1]) cudaFree(s.buf[1]);
     if (s.flags) cudaFree(s.flags);
     if (s.ev) cudaEventDestroy(s.ev);
+    if (s.ev_chunk) cudaEventDestroy(s.ev_chunk);
+    if (s.ev_join) cudaEventDestroy(s.ev_join);
+    if (s.stream2) { cudaStreamSynchronize(s.stream2); cudaStreamDestroy(s.stream2); }
     if (s.ctx) qb200_ctx_destroy(s.ctx);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
@@ -1046,6 +1259,11 @@ int qb200_sv_set_option(qb200_sv* sv, const char* key, int value) {
   else if (!std::strcmp(key, "reorder")) sv->reorder = value;
   else if (!std::strcmp(key, "push_kernel")) sv->push_kernel = value;
   else if (!std::strcmp(key, "push_ctas_per_sm")) sv->push_ctas_per_sm = value;
+  else if (!std::strcmp(key, "overlap")) sv->overlap = value;
+  else if (!std::strcmp(key, "overlap_chunks_log2")) sv->overlap_chunks_log2 = value;
+  else if (!std::strcmp(key, "overlap_max_gates")) sv->overlap_max_gates = value;
+  else if (!std::strcmp(key, "overlap_occ_reduce")) sv->overlap_occ_reduce = value;
+  else if (!std::strcmp(key, "overlap_ctas_per_sm")) sv->overlap_ctas_per_sm = value;
   else if (!std::strcmp(key, "barrier_flags")) {
     if (sv->mp && !value) return QB200_ERR_INVALID;  // events do not cross processes
     sv->barrier_flags = value;
@@ -1073,6 +1291,9 @@ int qb200_sv_get_stats(qb200_sv* sv, qb200_sv_stats* out) {
   out->bytes_sent_per_shard = sv->stats.bytes_sent_per_shard;
   out->exchange_ms = sv->stats.exchange_ms;
   out->barrier_wait_ms = sv->stats.wait_ms;
+  out->overlapped_swaps = sv->stats.overlapped_swaps;
+  out->overlapped_gate_passes = sv->stats.overlapped_gate_passes;
+  out->overlap_ms = sv->stats.overlap_ms;
   return QB200_OK;
 }
 
@@ -1271,7 +1492,21 @@ int qb200_sv_run(qb200_sv* sv, const qb200_gate* gates, uint64_t count) {
   }
   const std::vector<int64_t>& steps = sv->plan_steps;
   const uint64_t need = steps.size();
+  OverlapSpec spec;
+  plan_overlap(sv, gates, steps, 0, &spec);
   for (uint64_t w = 0; w < need;) {
+    if (spec.valid && w == spec.start) {
+      PushPlan pp;
+      const int prc = push_prepare(sv, spec.victims, spec.incoming, &pp);
+      if (prc == QB200_OK) {
+        SV_TRY(run_overlapped(sv, gates, steps, spec, pp));
+        w = spec.swap + 1 + 2 * spec.victims.size();
+        plan_overlap(sv, gates, steps, w, &spec);
+        continue;
+      }
+      if (prc != QB200_ERR_UNSUPPORTED) return prc;
+      spec.valid = false;   // no room for the spare buffers: plain gates, in-place exchange
+    }
     const int64_t v = steps[w++];
     if (v >= 0) {
       const qb200_gate& gt = gates[v];
@@ -1284,6 +1519,7 @@ int qb200_sv_run(qb200_sv* sv, const qb200_gate* gates, uint64_t count) {
       for (unsigned j = 0; j < k; ++j) iq[j] = (unsigned) steps[w + k + j];
       w += 2 * k;
       SV_TRY(exchange(sv, vq, iq, k));
+      plan_overlap(sv, gates, steps, w, &spec);
     }
   }
   return QB200_OK;

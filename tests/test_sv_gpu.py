@@ -148,6 +148,37 @@ def test_run_matches_unsharded_oracle(oracle, shards, swap_mode, reorder):
     st.close(); st2.close()
 
 
+@pytest.mark.parametrize("shards,chunks_log2,dtype", [(2, 2, np.float32), (4, 1, np.float32), (4, 3, np.float32),
+                                                      (8, 2, np.float32), (2, 2, np.float64), (4, 3, np.float64)])
+def test_exchange_overlapped_with_the_last_gates_of_the_epoch(oracle, shards, chunks_log2, dtype):
+    """qb200_sv_run, option overlap (csrc/sharded.cu run_overlapped): the last gate passes before an exchange run
+    chunk by chunk -- the chunk bits as extra controls -- and every chunk is pushed on a second stream while the
+    gates work on the next one.  Same schedule; a pass under extra controls may take another kernel of the
+    dispatcher (different summation order), so the state equals the one of overlap = 0, and the oracle's, to
+    round-off."""
+    g = shards.bit_length() - 1
+    n = 17 + g
+    cd = np.complex64 if dtype == np.float32 else np.complex128
+    ops = random_ops(n, 60, seed=31 + shards + chunks_log2, max_targets=5 if dtype == np.float32 else 4)
+    want = oracle_run(oracle, n, ops, cd)
+    states = []
+    for overlap in (1, 0):
+        st = make(shards, n, dtype, overlap=overlap, overlap_chunks_log2=chunks_log2)
+        st.SetStateZero()
+        st.Run(ops)
+        stats = st.stats()
+        assert stats["swaps"] >= 1 and stats["gate_passes"] == len(ops)
+        if overlap:
+            assert stats["overlapped_swaps"] >= 1 and stats["overlapped_gate_passes"] >= stats["overlapped_swaps"]
+        else:
+            assert stats["overlapped_swaps"] == 0
+        states.append(st.to_numpy())
+        st.close()
+    tol = 3e-6 if dtype == np.float32 else 1e-13
+    assert np.abs(states[0] - want).max() < tol
+    assert np.abs(states[0] - states[1]).max() < tol
+
+
 @pytest.mark.parametrize("push_kernel", [0, 1])
 def test_run_fp64(oracle, push_kernel):
     n, shards = 13, 4
