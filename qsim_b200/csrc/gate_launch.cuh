@@ -40,6 +40,14 @@ template <typename FP, int G> constexpr int min_blocks() {
 
 constexpr uint32_t kExpectMaxBlocks = kNumSMs * 8;
 
+// Largest shared-memory carveout for the warp-tile kernel: k_gate_tile<4> 3.43 -> 2.92 ms per pass at 30 qubits.  (The
+// tensor-core kernels want the opposite: their per-thread 64-byte row loads rely on L1 sector merging, 2.82 -> 3.34 ms
+// with the largest carveout.)
+template <typename K>
+inline void prefer_max_smem(K kern) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 // resident blocks per SM of a kernel (queried once per instantiation)
 template <typename K>
 int resident_blocks(K kern, int threads) {
@@ -82,6 +90,7 @@ int launch_tile(qb200_ctx* ctx, float* st, const TileGeom& t, const float* m) {
   static PerDevice occ_cache;
   const int occ = occ_cache.get(ctx, [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    prefer_max_smem(kern);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TNT, smem) != cudaSuccess || nb < 1) {
       (void) cudaGetLastError();
@@ -164,7 +173,8 @@ int launch_reg(qb200_ctx* ctx, FP* st, const Geom& g, const FP* m, double* out) 
     if constexpr (kCanPrefetch) {
       if (ctx->tune.prefetch != 0) {
         auto kern = k_gate_reg<FP, G, MODE, UNROLL, false, true, NT, MINB, Mat>;
-        static const int occ = resident_blocks(kern, NT);
+        static PerDevice occ_cache;
+        const int occ = occ_cache.get(ctx, [&] { return resident_blocks(kern, NT); });
         const uint64_t persistent = uint64_t(grid_sms(ctx)) * grid_occ(ctx, occ);
         const uint32_t blocks = (uint32_t) (blocks64 < persistent ? blocks64 : persistent);
         kern<<<blocks, NT, 0, ctx->stream>>>(st, g, mat, nullptr);

@@ -177,12 +177,17 @@ __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.
 }  // namespace bulk
 
 // NT threads: 256 when the exchange runs alone; 64 when gate kernels run beside it (the threads only do the
-// shared->shared scatter; 64 x 31 registers fit next to three resident k_gate_tca<4> CTAs of 256 x 80).
+// shared->shared scatter; 64 x 32 registers fit next to three resident k_gate_tca<4> CTAs of 256 x 80).
+// `sin` input stages (a ring, loads issued sin - 1 or sin - 2 tiles ahead): beside gate kernels that keep HBM
+// saturated a bulk load takes several microseconds, so the slim variant runs with a deep ring.  Without victim bits
+// inside the tile (kl = 0) a tile needs no sorting: it is stored straight from its input stage, no output stages.
+constexpr int kMaxPushStages = 12;
+
 template <typename FP, int NT>
 __global__ void __launch_bounds__(NT)
-k_remap_push_tma(const FP* __restrict__ src, const __grid_constant__ RemapGeom g) {
+k_remap_push_tma(const FP* __restrict__ src, const __grid_constant__ RemapGeom g, const uint32_t sin) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full[2];
+  __shared__ __align__(8) uint64_t full[kMaxPushStages];
   constexpr int APT = sizeof(FP) == 4 ? 2 : 1;
   const uint32_t tile_amps = 1u << g.T;
   const uint32_t tile_bytes = tile_amps * 2 * sizeof(FP);
@@ -190,13 +195,14 @@ k_remap_push_tma(const FP* __restrict__ src, const __grid_constant__ RemapGeom g
   const uint32_t kh = g.k - g.kl;
   const uint32_t sub_bits = g.T - g.kl;
   const uint32_t my_high = g.my >> g.kl;
-  unsigned char* const in_p = smem_raw;                       // 2 input stages
-  unsigned char* const out_p = smem_raw + 2 * tile_bytes;     // 2 output stages
+  const bool sort = g.kl != 0;
+  const uint32_t ahead = sort ? sin - 1 : sin - 2;             // tiles a load is issued ahead of its use
+  unsigned char* const in_p = smem_raw;                        // sin input stages
+  unsigned char* const out_p = smem_raw + sin * tile_bytes;    // 2 output stages (sort only)
   const uint32_t in_s = bulk::smem_addr(in_p), out_s = bulk::smem_addr(out_p);
   const uint32_t full_s = bulk::smem_addr(&full[0]);
   if (threadIdx.x == 0) {
-    bulk::mbar_init(full_s, 1);
-    bulk::mbar_init(full_s + 8, 1);
+    for (uint32_t i = 0; i < sin; ++i) bulk::mbar_init(full_s + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -211,64 +217,75 @@ k_remap_push_tma(const FP* __restrict__ src, const __grid_constant__ RemapGeom g
     }
     return tau;
   };
-
-  uint64_t cc = blockIdx.x;
-  if (threadIdx.x == 0 && cc < g.walk) {
+  auto issue_load = [&](uint64_t cc, uint32_t stage) {
     uint32_t vh;
     const uint64_t tau = tile_index(chunk_counter(cc, g), &vh);
-    bulk::mbar_expect_tx(full_s, tile_bytes);
-    bulk::load(in_s, reinterpret_cast<const unsigned char*>(src) + tau * tile_bytes, tile_bytes, full_s);
+    bulk::mbar_expect_tx(full_s + 8 * stage, tile_bytes);
+    bulk::load(in_s + stage * tile_bytes, reinterpret_cast<const unsigned char*>(src) + tau * tile_bytes, tile_bytes,
+               full_s + 8 * stage);
+  };
+
+  uint64_t cc = blockIdx.x;
+  if (threadIdx.x == 0) {
+    uint64_t cp = cc;
+    for (uint32_t i = 0; i < ahead && cp < g.walk; ++i, cp += gridDim.x) issue_load(cp, i);
   }
+  uint32_t st_in = 0, ph_in = 0;                              // input stage of this iteration and its mbarrier phase
+  uint32_t st_ld = ahead % sin;                               // stage the look-ahead load of this iteration goes to
   for (uint32_t it = 0; cc < g.walk; cc += gridDim.x, ++it) {
     const uint32_t s = it & 1;
     const uint64_t c = chunk_counter(cc, g);
     if (threadIdx.x == 0) {
-      const uint64_t cn = cc + gridDim.x;
-      if (cn < g.walk) {  // input stage s^1 was consumed by the scatter of the previous iteration
-        uint32_t vh;
-        const uint64_t tau = tile_index(chunk_counter(cn, g), &vh);
-        bulk::mbar_expect_tx(full_s + 8 * (s ^ 1), tile_bytes);
-        bulk::load(in_s + (s ^ 1) * tile_bytes, reinterpret_cast<const unsigned char*>(src) + tau * tile_bytes, tile_bytes,
-                   full_s + 8 * (s ^ 1));
-      }
-      bulk::wait_read<1>();  // the stores issued two iterations ago have read output stage s
+      // sort: the stores issued two iterations ago have read output stage s; the look-ahead stage was emptied by the
+      // scatter of the previous iteration.  No sort: the look-ahead stage was the source of the stores of two
+      // iterations ago.
+      bulk::wait_read<1>();
+      const uint64_t cn = cc + uint64_t{ahead} * gridDim.x;
+      if (cn < g.walk) issue_load(cn, st_ld);
     }
-    __syncthreads();
-    bulk::mbar_wait(full_s + 8 * s, (it >> 1) & 1);
-    const unsigned char* const tin = in_p + s * tile_bytes;
-    unsigned char* const tout = out_p + s * tile_bytes;
-    for (uint32_t i0 = threadIdx.x; i0 < items; i0 += NT) {
-      const uint4 x = reinterpret_cast<const uint4*>(tin)[i0];
+    if (sort) __syncthreads();
+    if (sort || threadIdx.x == 0) bulk::mbar_wait(full_s + 8 * st_in, ph_in);
+    uint32_t v_high;
+    (void) tile_index(c, &v_high);
+    const uint64_t packed_high = c >> kh;
+    const uint64_t d = ((uint64_t{g.my} << (g.nl - g.k)) | (packed_high << sub_bits)) * 2 * sizeof(FP);
+    if (sort) {
+      const unsigned char* const tin = in_p + st_in * tile_bytes;
+      unsigned char* const tout = out_p + s * tile_bytes;
+      for (uint32_t i0 = threadIdx.x; i0 < items; i0 += NT) {
+        const uint4 x = reinterpret_cast<const uint4*>(tin)[i0];
 #pragma unroll
-      for (int a = 0; a < APT; ++a) {
-        uint32_t i = i0 * APT + a, v = 0, r = i;
-        for (int j = (int) g.kl - 1; j >= 0; --j) {
-          const uint32_t b = g.lbits[j];
-          v |= ((r >> b) & 1u) << j;
-          r = ((r >> (b + 1)) << b) | (r & ((1u << b) - 1));
-        }
-        const uint32_t p = (v << sub_bits) | r;
-        if constexpr (APT == 2) {
-          reinterpret_cast<uint2*>(tout)[p] = a == 0 ? make_uint2(x.x, x.y) : make_uint2(x.z, x.w);
-        } else {
-          reinterpret_cast<uint4*>(tout)[p] = x;
+        for (int a = 0; a < APT; ++a) {
+          uint32_t i = i0 * APT + a, v = 0, r = i;
+          for (int j = (int) g.kl - 1; j >= 0; --j) {
+            const uint32_t b = g.lbits[j];
+            v |= ((r >> b) & 1u) << j;
+            r = ((r >> (b + 1)) << b) | (r & ((1u << b) - 1));
+          }
+          const uint32_t p = (v << sub_bits) | r;
+          if constexpr (APT == 2) {
+            reinterpret_cast<uint2*>(tout)[p] = a == 0 ? make_uint2(x.x, x.y) : make_uint2(x.z, x.w);
+          } else {
+            reinterpret_cast<uint4*>(tout)[p] = x;
+          }
         }
       }
-    }
-    bulk::fence_async();   // generic-proxy writes to shared memory -> visible to the bulk-copy engine
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t v_high;
-      (void) tile_index(c, &v_high);
-      const uint64_t packed_high = c >> kh;
-      const uint32_t run_bytes = (1u << sub_bits) * 2 * sizeof(FP);
-      const uint64_t d = ((uint64_t{g.my} << (g.nl - g.k)) | (packed_high << sub_bits)) * 2 * sizeof(FP);
-      for (uint32_t vl = 0; vl < (1u << g.kl); ++vl) {
-        const uint32_t v = vl | (v_high << g.kl);
-        bulk::store(reinterpret_cast<unsigned char*>(g.dst[v]) + d, out_s + s * tile_bytes + vl * run_bytes, run_bytes);
+      bulk::fence_async();   // generic-proxy writes to shared memory -> visible to the bulk-copy engine
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const uint32_t run_bytes = (1u << sub_bits) * 2 * sizeof(FP);
+        for (uint32_t vl = 0; vl < (1u << g.kl); ++vl) {
+          const uint32_t v = vl | (v_high << g.kl);
+          bulk::store(reinterpret_cast<unsigned char*>(g.dst[v]) + d, out_s + s * tile_bytes + vl * run_bytes, run_bytes);
+        }
+        bulk::commit();
       }
+    } else if (threadIdx.x == 0) {
+      bulk::store(reinterpret_cast<unsigned char*>(g.dst[v_high]) + d, in_s + st_in * tile_bytes, tile_bytes);
       bulk::commit();
     }
+    if (++st_in == sin) { st_in = 0; ph_in ^= 1; }
+    if (++st_ld == sin) st_ld = 0;
   }
   if (threadIdx.x == 0) bulk::wait_all();
 }
@@ -368,9 +385,13 @@ struct qb200_sv {
   int push_kernel = 1;                   // 1: bulk-copy engine (k_remap_push_tma, default); 0: st.global from registers
   int push_ctas_per_sm = 0;              // 0 = default of the chosen kernel
   int overlap_ctas_per_sm = 0;           // CTAs per SM of the slim push kernel that runs beside gates (0 = 1)
-  int overlap = 1;                       // qb200_sv_run: the last gates of an epoch run beside its exchange, chunk by chunk
+  int overlap_smem_kb = 0;               // ... and its shared memory per CTA (0 = 16 KB)
+  int overlap_tile_bits = 9;             // ... which moves tiles of 2^this amplitudes (4 KB in fp32)
+  int overlap = 0;                       // qb200_sv_run: the last gates of an epoch run beside its exchange, chunk by chunk
+                                         // (off by default: measured no gain on B200, profiles/r02_overlap_trace.txt)
   int overlap_chunks_log2 = 2;           // 2^this chunks per shard
   int overlap_max_gates = 6;             // gate passes pipelined against one exchange (enough to cover it, see run_overlapped)
+  int overlap_trace = 0;                 // 1: print a device timeline of the next overlapped exchange (first local shard) to stderr
   int overlap_occ_reduce = 0;            // resident gate CTAs per SM given up while the slim push kernel runs beside them
   SvStats stats;
   std::vector<uint64_t> plan_key;        // gate structure + global set the cached schedule was made for
@@ -768,12 +789,12 @@ struct PushPlan {
 
 // QB200_ERR_UNSUPPORTED: this exchange cannot go out of place (tiny shard or no room for the spare buffers)
 static int push_prepare(qb200_sv* sv, const std::vector<unsigned>& victims, const std::vector<unsigned>& incoming,
-                        PushPlan* pp) {
+                        PushPlan* pp, unsigned tile_bits = kTileBits) {
   const unsigned k = (unsigned) victims.size();
   if (sv->swap_mode == 0) return QB200_ERR_UNSUPPORTED;
   // the push kernel sorts tiles of 2^T amplitudes by the victim bits they contain: every destination run must
   // hold at least one 16-byte item (a shard of a handful of qubits with all of them victims does not qualify)
-  const unsigned T = std::min<unsigned>(kTileBits, sv->nl);
+  const unsigned T = std::min<unsigned>(tile_bits, sv->nl);
   unsigned kl = 0;
   for (unsigned j = 0; j < k; ++j) kl += sv->pos[victims[j]] < T;
   if (T < kl + (sv->dtype == QB200_F32 ? 1u : 0u)) return sv->swap_mode == 1 ? QB200_ERR_INVALID : QB200_ERR_UNSUPPORTED;
@@ -797,15 +818,28 @@ static int push_prepare(qb200_sv* sv, const std::vector<unsigned>& victims, cons
   return QB200_OK;
 }
 
+// shared memory of a push CTA: `budget` bytes cut into input stages (+ 2 output stages when tiles are sorted)
+static uint32_t push_stages(const RemapGeom& rg, size_t tile_bytes, size_t budget) {
+  const size_t out = rg.kl ? 2 * tile_bytes : 0;
+  size_t sin = budget > out ? (budget - out) / tile_bytes : 0;
+  const size_t lo = rg.kl ? 2 : 3;
+  if (sin < lo) sin = lo;
+  if (sin > (size_t) kMaxPushStages) sin = kMaxPushStages;
+  return (uint32_t) sin;
+}
+
 template <typename FP, int NT>
-static void launch_push_tma(qb200_sv* sv, Shard& s, const RemapGeom& rg, size_t smem4, int ctas_per_sm, cudaStream_t stream) {
+static void launch_push_tma(qb200_sv* sv, Shard& s, const RemapGeom& rg, size_t tile_bytes, size_t budget, int ctas_per_sm,
+                            cudaStream_t stream) {
   static PerDevice attr;
   attr.get(s.ctx, [&] {
-    cudaFuncSetAttribute(k_remap_push_tma<FP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (4 * 16384 * sizeof(FP) / 4));
+    cudaFuncSetAttribute(k_remap_push_tma<FP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     return 1;
   });
+  const uint32_t sin = push_stages(rg, tile_bytes, budget);
+  const size_t smem = (sin + (rg.kl ? 2 : 0)) * tile_bytes;
   const uint64_t b2 = std::min<uint64_t>(rg.walk, uint64_t{kNumSMs} * ctas_per_sm);
-  k_remap_push_tma<FP, NT><<<(uint32_t) b2, NT, smem4, stream>>>((const FP*) s.buf[sv->cur], rg);
+  k_remap_push_tma<FP, NT><<<(uint32_t) b2, NT, smem, stream>>>((const FP*) s.buf[sv->cur], rg, sin);
 }
 
 // one shard's push (the whole shard, or the chunk pp.rg describes) on `stream`; slim = the 64-thread variant that
@@ -817,17 +851,21 @@ static int push_launch(qb200_sv* sv, Shard& s, PushPlan& pp, cudaStream_t stream
   rg.my = pick_bits(s.rank, pp.gb, pp.k);
   for (unsigned v = 0; v < (1u << pp.k); ++v) rg.dst[v] = sv->peer_buf[nb][with_bits(s.rank, pp.gb, pp.k, v)];
   if (sv->push_kernel == 1) {
-    // bulk-copy variant: 2 + 2 stages of one tile each
-    const size_t smem4 = 4 * pp.smem;
     const bool f32 = sv->dtype == QB200_F32;
     if (slim) {
+      // A small footprint matters more than a deep ring: the SM's L1 / shared split follows the resident CTAs, and the
+      // tensor-core gate kernels lose 18 % when a neighbour forces the largest carveout (their 64-byte row loads live
+      // on L1 sector merging) -- 16 KB (four 4 KB tiles) stay inside the carveout three k_gate_tca<4> CTAs get anyway.
       const int per_sm = sv->overlap_ctas_per_sm > 0 ? sv->overlap_ctas_per_sm : 1;
-      if (f32) launch_push_tma<float, 64>(sv, s, rg, smem4, per_sm, stream);
-      else launch_push_tma<double, 64>(sv, s, rg, smem4, per_sm, stream);
+      const size_t budget = size_t{1024} * (sv->overlap_smem_kb > 0 ? sv->overlap_smem_kb : 16);
+      if (f32) launch_push_tma<float, 64>(sv, s, rg, pp.smem, budget, per_sm, stream);
+      else launch_push_tma<double, 64>(sv, s, rg, pp.smem, budget, per_sm, stream);
     } else {
+      // alone: three CTAs per SM (fp64: one) with 4 tiles each
       const int per_sm = sv->push_ctas_per_sm > 0 ? sv->push_ctas_per_sm : (f32 ? 3 : 1);
-      if (f32) launch_push_tma<float, kRemapThreads>(sv, s, rg, smem4, per_sm, stream);
-      else launch_push_tma<double, kRemapThreads>(sv, s, rg, smem4, per_sm, stream);
+      const size_t budget = 4 * pp.smem;
+      if (f32) launch_push_tma<float, kRemapThreads>(sv, s, rg, pp.smem, budget, per_sm, stream);
+      else launch_push_tma<double, kRemapThreads>(sv, s, rg, pp.smem, budget, per_sm, stream);
     }
   } else {
     const uint64_t blocks = std::min<uint64_t>(rg.walk, uint64_t{kNumSMs} * 6);
@@ -1034,13 +1072,27 @@ static int run_overlapped(qb200_sv* sv, const qb200_gate* gates, const std::vect
   sv->ev_overlapped[sv->ev_used] = 1;
   for (auto& s : sv->sh) s.ctx->occ_reduce = sv->overlap_occ_reduce;
   int rc = QB200_OK;
+  // debugging aid: CUDA events around every chunk's gates (main stream) and push (second stream) of the first shard
+  std::vector<cudaEvent_t> tr;
+  const bool trace = sv->overlap_trace != 0;
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    DevScope d(sv->sh[0].device);
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tr.push_back(e);
+  };
   for (unsigned v = 0; v < (1u << c) && rc == QB200_OK; ++v) {
+    mark(sv->sh[0].stream);
     for (uint64_t i = spec.start; i < spec.swap && rc == QB200_OK; ++i) {
       const qb200_gate& gt = gates[steps[i]];
       if (v == 0) touch(sv, gt.qs, gt.num_targets);
       rc = local_gate(sv, gt.qs, gt.num_targets, gt.cqs, gt.num_controls, gt.cvals, gt.matrix, false, nullptr,
                       spec.chunk_bits, c, v);
+      if (trace && v == 0) fprintf(stderr, "overlap trace: gate %s\n", sv->sh[0].ctx->last_kernel);
     }
+    mark(sv->sh[0].stream);
     rg.cval = v;
     for (auto& s : sv->sh) {
       if (rc != QB200_OK) break;
@@ -1050,9 +1102,22 @@ static int run_overlapped(qb200_sv* sv, const qb200_gate* gates, const std::vect
         rc = QB200_ERR_CUDA;
         break;
       }
+      if (&s == &sv->sh[0]) mark(s.stream2);
       rc = push_launch(sv, s, pp, s.stream2, true);
+      if (&s == &sv->sh[0]) mark(s.stream2);
     }
   }
+  if (trace && rc == QB200_OK) {
+    sv->overlap_trace = 0;
+    sync_all(sv);
+    { DevScope d(sv->sh[0].device); cudaStreamSynchronize(sv->sh[0].stream2); }
+    for (unsigned v = 0; v < (1u << c); ++v) {
+      float t[4] = {};
+      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tr[0], tr[4 * v + i]);
+      fprintf(stderr, "overlap trace: chunk %u gates %.3f..%.3f ms, push %.3f..%.3f ms\n", v, t[0], t[1], t[2], t[3]);
+    }
+  }
+  for (auto e : tr) cudaEventDestroy(e);
   for (auto& s : sv->sh) {
     s.ctx->occ_reduce = 0;
     DevScope d(s.device);
@@ -1263,7 +1328,10 @@ int qb200_sv_set_option(qb200_sv* sv, const char* key, int value) {
   else if (!std::strcmp(key, "overlap_chunks_log2")) sv->overlap_chunks_log2 = value;
   else if (!std::strcmp(key, "overlap_max_gates")) sv->overlap_max_gates = value;
   else if (!std::strcmp(key, "overlap_occ_reduce")) sv->overlap_occ_reduce = value;
+  else if (!std::strcmp(key, "overlap_trace")) sv->overlap_trace = value;
   else if (!std::strcmp(key, "overlap_ctas_per_sm")) sv->overlap_ctas_per_sm = value;
+  else if (!std::strcmp(key, "overlap_smem_kb")) sv->overlap_smem_kb = value;
+  else if (!std::strcmp(key, "overlap_tile_bits")) sv->overlap_tile_bits = value;
   else if (!std::strcmp(key, "barrier_flags")) {
     if (sv->mp && !value) return QB200_ERR_INVALID;  // events do not cross processes
     sv->barrier_flags = value;
@@ -1497,7 +1565,9 @@ int qb200_sv_run(qb200_sv* sv, const qb200_gate* gates, uint64_t count) {
   for (uint64_t w = 0; w < need;) {
     if (spec.valid && w == spec.start) {
       PushPlan pp;
-      const int prc = push_prepare(sv, spec.victims, spec.incoming, &pp);
+      // small tiles: the slim push kernel must not push the SMs into a larger shared-memory carveout (see push_launch)
+      const unsigned tb = (unsigned) std::min<int>(kTileBits, std::max(8, sv->overlap_tile_bits));
+      const int prc = push_prepare(sv, spec.victims, spec.incoming, &pp, tb);
       if (prc == QB200_OK) {
         SV_TRY(run_overlapped(sv, gates, steps, spec, pp));
         w = spec.swap + 1 + 2 * spec.victims.size();
