@@ -204,6 +204,14 @@ int qb200_sample(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubi
 /* Host helper = GenerateRandomValues<double> (lib/util.h:67-85): std::mt19937(seed),
  * uniform_real_distribution(0,max_value), sorted ascending. */
 int qb200_generate_random_values(uint64_t num_samples, unsigned seed, double max_value, double* out);
+/* The same values drawn and sorted ON THE DEVICE (the reference's TODO at lib/statespace_cuda.h:292): a device
+ * MT19937 + libstdc++'s uniform_real_distribution<double> arithmetic + radix sort, bit-identical to the host helper
+ * (csrc/sample_rng.cu).  qb200_sample_seeded = Sample(state, num_samples, seed) with `norm` = the caller's Norm(state):
+ * no host random numbers, no host sort, no host->device copy; same indices as qb200_sample on the host values.
+ * qb200_generate_random_values_device copies the sorted values to host memory `out` (tests). */
+int qb200_sample_seeded(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits, uint64_t num_samples,
+                        unsigned seed, double norm, uint64_t* out);
+int qb200_generate_random_values_device(qb200_ctx* ctx, uint64_t num_samples, unsigned seed, double max_value, double* out);
 /* PartialNorms (:331-355): the state is cut into qb200_partial_norms_count(n)
  * equal contiguous chunks; out[m] = sum |amp|^2 over chunk m. */
 uint64_t qb200_partial_norms_count(unsigned num_qubits);

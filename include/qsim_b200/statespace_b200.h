@@ -7,6 +7,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdint>
+#include <type_traits>
 #include <vector>
 
 #include "statespace.h"  // reference: lib/statespace.h
@@ -116,12 +117,19 @@ class StateSpaceB200 : public StateSpace<StateSpaceB200<FP>, VectorSpaceB200, FP
     std::vector<uint64_t> bitstrings;
     if (num_samples > 0) {
       double norm = Norm(state);
-      // host RNG exactly as the reference draws it (lib/statespace_cuda.h:293)
-      auto rs = GenerateRandomValues<DistrRealType>(num_samples, seed, norm);
-      std::vector<double> rsd(rs.begin(), rs.begin() + num_samples);
       bitstrings.resize(num_samples, 0);
-      QB200_CHECK(this->ctx(), qb200_sample(this->ctx(), kDT, state.get(), state.num_qubits(), rsd.data(),
-                                            num_samples, bitstrings.data()));
+      if (std::is_same<DistrRealType, double>::value) {
+        // the reference's TODO (lib/statespace_cuda.h:292): the values GenerateRandomValues<double> would draw on
+        // the host are drawn and sorted on the device, bit for bit (csrc/sample_rng.cu)
+        QB200_CHECK(this->ctx(), qb200_sample_seeded(this->ctx(), kDT, state.get(), state.num_qubits(), num_samples,
+                                                     seed, norm, bitstrings.data()));
+      } else {
+        // any other distribution type: host RNG exactly as the reference draws it (lib/statespace_cuda.h:293)
+        auto rs = GenerateRandomValues<DistrRealType>(num_samples, seed, norm);
+        std::vector<double> rsd(rs.begin(), rs.begin() + num_samples);
+        QB200_CHECK(this->ctx(), qb200_sample(this->ctx(), kDT, state.get(), state.num_qubits(), rsd.data(),
+                                              num_samples, bitstrings.data()));
+      }
     }
     return bitstrings;
   }

@@ -253,13 +253,28 @@ class StateSpaceB200(_Base):
                                                            rs.ctypes.data_as(C.POINTER(C.c_double))), "GenerateRandomValues")
         return rs
 
-    def Sample(self, state: State, num_samples: int, seed: int) -> np.ndarray:
-        """lib/statespace_cuda.h:243-312: norm -> sorted host random values -> device search."""
+    def GenerateRandomValuesOnDevice(self, num_samples: int, seed: int, max_value: float) -> np.ndarray:
+        """The same sorted values drawn by the device Mersenne Twister (csrc/sample_rng.cu), copied back."""
+        rs = np.empty(num_samples, dtype=np.float64)
+        self._check(self._lib.qb200_generate_random_values_device(self._ctx, num_samples, seed, max_value,
+                                                                  rs.ctypes.data_as(C.POINTER(C.c_double))),
+                    "GenerateRandomValuesOnDevice")
+        return rs
+
+    def Sample(self, state: State, num_samples: int, seed: int, host_rng: bool = False) -> np.ndarray:
+        """lib/statespace_cuda.h:243-312: norm -> sorted random values -> device search.  The values are drawn on
+        the device (the reference's TODO at :292; bit-identical to the host draw, csrc/sample_rng.cu) unless
+        host_rng asks for the reference's host path."""
         out = np.zeros(num_samples, dtype=np.uint64)
         if num_samples > 0:
             norm = self.Norm(state)
-            rs = self.GenerateRandomValues(num_samples, seed, norm)
-            self.SampleWithValues(state, rs, out)
+            if host_rng:
+                rs = self.GenerateRandomValues(num_samples, seed, norm)
+                self.SampleWithValues(state, rs, out)
+            else:
+                self._check(self._lib.qb200_sample_seeded(self._ctx, self._dt, state.get(), state.num_qubits(),
+                                                          num_samples, seed, norm,
+                                                          out.ctypes.data_as(C.POINTER(C.c_uint64))), "Sample")
         return out
 
     def SampleWithValues(self, state: State, sorted_rs: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -354,23 +354,38 @@ int find_measured_bits(qb200_ctx* ctx, const FP* st, unsigned n, uint64_t m, dou
   return QB200_OK;
 }
 
+// sample_rng.cu
+size_t sorted_uniform_temp_bytes(uint64_t ns);
+int sorted_uniform_device(qb200_ctx* ctx, unsigned seed, uint64_t ns, double max_value, double* d_draws,
+                          double* d_sorted, void* d_temp, size_t temp_bytes);
+
+// sorted_rs != nullptr: the caller's sorted values (host memory); else they are drawn on the device from
+// (seed, max_value) exactly as GenerateRandomValues<double> draws them (sample_rng.cu).
 template <typename FP>
-int sample(qb200_ctx* ctx, const FP* st, unsigned n, const double* sorted_rs, uint64_t ns,
-           uint64_t* out) {
+int sample(qb200_ctx* ctx, const FP* st, unsigned n, const double* sorted_rs, unsigned seed, double max_value,
+           uint64_t ns, uint64_t* out) {
   if (!ctx || !st || n > kMaxQubits || !aligned_ok<FP>(st)) return QB200_ERR_INVALID;
   if (ns == 0) return QB200_OK;
-  if (!sorted_rs || !out) return QB200_ERR_INVALID;
+  if (!out) return QB200_ERR_INVALID;
   DeviceGuard guard(ctx);
   const uint64_t chunk_amps = uint64_t{1} << chunk_bits(n);
   const uint64_t nchunks = (uint64_t{1} << n) / chunk_amps;
-  const size_t bytes = (2 * nchunks + 1 + 2 * ns) * sizeof(double);
+  const size_t temp_bytes = sorted_rs ? 0 : sorted_uniform_temp_bytes(ns);
+  const size_t bytes = (2 * nchunks + 1 + 2 * ns + (sorted_rs ? 0 : ns)) * sizeof(double) + 256 + temp_bytes;
   int rc = ensure_scratch(ctx, bytes);
   if (rc) return rc;
   double* d_sums = (double*) ctx->scratch;
   double* d_prefix = d_sums + nchunks;
   double* d_rs = d_prefix + nchunks + 1;
   uint64_t* d_out = (uint64_t*) (d_rs + ns);
-  QB_CUDA(ctx, cudaMemcpyAsync(d_rs, sorted_rs, ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (sorted_rs) {
+    QB_CUDA(ctx, cudaMemcpyAsync(d_rs, sorted_rs, ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    double* d_draws = (double*) (d_out + ns);
+    void* d_temp = (void*) (((uintptr_t) (d_draws + ns) + 255) & ~uintptr_t{255});
+    rc = sorted_uniform_device(ctx, seed, ns, max_value, d_draws, d_rs, d_temp, temp_bytes);
+    if (rc) return rc;
+  }
   rc = chunk_norms_device(ctx, st, n, d_sums);
   if (rc) return rc;
   k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(d_sums, nchunks, d_prefix);
@@ -514,8 +529,32 @@ int qb200_norm(qb200_ctx* ctx, int dtype, const void* state, unsigned n, double*
 
 int qb200_sample(qb200_ctx* ctx, int dtype, const void* state, unsigned n, const double* sorted_rs,
                  uint64_t num_samples, uint64_t* out) {
-  QB_DISPATCH(dtype, sample<FP>(ctx, (const FP*) state, n, sorted_rs, num_samples, out),
-              sample<FP>(ctx, (const FP*) state, n, sorted_rs, num_samples, out));
+  if (num_samples && !sorted_rs) return QB200_ERR_INVALID;
+  QB_DISPATCH(dtype, sample<FP>(ctx, (const FP*) state, n, sorted_rs, 0, 0.0, num_samples, out),
+              sample<FP>(ctx, (const FP*) state, n, sorted_rs, 0, 0.0, num_samples, out));
+}
+
+int qb200_sample_seeded(qb200_ctx* ctx, int dtype, const void* state, unsigned n, uint64_t num_samples, unsigned seed,
+                        double norm, uint64_t* out) {
+  QB_DISPATCH(dtype, sample<FP>(ctx, (const FP*) state, n, nullptr, seed, norm, num_samples, out),
+              sample<FP>(ctx, (const FP*) state, n, nullptr, seed, norm, num_samples, out));
+}
+
+int qb200_generate_random_values_device(qb200_ctx* ctx, uint64_t num_samples, unsigned seed, double max_value, double* out) {
+  if (!ctx || (num_samples && !out)) return QB200_ERR_INVALID;
+  if (num_samples == 0) return QB200_OK;
+  DeviceGuard guard(ctx);
+  const size_t temp_bytes = sorted_uniform_temp_bytes(num_samples);
+  int rc = ensure_scratch(ctx, 2 * num_samples * sizeof(double) + 256 + temp_bytes);
+  if (rc) return rc;
+  double* d_draws = (double*) ctx->scratch;
+  double* d_sorted = d_draws + num_samples;
+  void* d_temp = (void*) (((uintptr_t) (d_sorted + num_samples) + 255) & ~uintptr_t{255});
+  rc = sorted_uniform_device(ctx, seed, num_samples, max_value, d_draws, d_sorted, d_temp, temp_bytes);
+  if (rc) return rc;
+  QB_CUDA(ctx, cudaMemcpyAsync(out, d_sorted, num_samples * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return QB200_OK;
 }
 
 int qb200_generate_random_values(uint64_t num_samples, unsigned seed, double max_value, double* out) {

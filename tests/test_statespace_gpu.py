@@ -163,6 +163,36 @@ def test_generate_random_values_is_reference_sequence():
     assert np.allclose(rs, want, rtol=0, atol=1e-16)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 12345, 2 ** 32 - 1])
+def test_device_random_values_are_the_host_sequence_bit_for_bit(seed):
+    """csrc/sample_rng.cu: device MT19937 + libstdc++'s uniform_real_distribution<double> arithmetic + radix sort
+    against GenerateRandomValues<double> (lib/util.h:67-85, std::mt19937 on the host): identical doubles for counts
+    around the 312-draws-per-twist boundary, for many twists, and for max_value != 1."""
+    ss = make(np.complex64)
+    for num, mx in [(1, 1.0), (5, 1.0), (311, 0.73), (312, 1.0), (313, 3.0), (624, 1.0 - 2.0 ** -30), (1000, 0.999999),
+                    (100003, 1.0000001)]:
+        host = ss.GenerateRandomValues(num, seed, mx)
+        dev = ss.GenerateRandomValuesOnDevice(num, seed, mx)
+        assert np.array_equal(host.view(np.uint64), dev.view(np.uint64)), (num, mx)
+
+
+@pytest.mark.parametrize("cdt", DTYPES)
+def test_sample_with_device_rng_equals_the_host_rng_path(oracle, cdt):
+    """Sample(state, m, seed) draws its values on the device (the reference's TODO, lib/statespace_cuda.h:292):
+    same indices as the host-RNG path and as the oracle's serial scan over the host values."""
+    ss = make(cdt)
+    n = 15
+    h = random_state(n, cdt, 21)
+    st = ss.Create(n)
+    ss.from_numpy(h, st)
+    for num, seed in [(1, 3), (777, 0), (50000, 99)]:
+        dev = ss.Sample(st, num, seed)
+        host = ss.Sample(st, num, seed, host_rng=True)
+        assert np.array_equal(dev, host)
+        want = oracle.sample(h, ss.GenerateRandomValues(num, seed, ss.Norm(st)))
+        assert np.count_nonzero(dev != want) <= 2   # a value within round-off of a cumulative sum may land next door
+
+
 @pytest.mark.parametrize("cdt", DTYPES)
 @pytest.mark.parametrize("n", [1, 5, 13, 16])
 def test_measure_matches_oracle(oracle, cdt, n):
