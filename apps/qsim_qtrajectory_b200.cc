@@ -81,12 +81,13 @@ struct Options {
   unsigned workers = 1;
   unsigned prefix = 1;            // 1: share the noiseless prefix between trajectories (B200 backend)
   std::string channel = "depolarize";  // or "amplitude_damp" (gamma = p)
+  int kraus_groups = 1;                // -k: all Kraus probabilities of a non-unitary channel from one read pass
 };
 
 Options Parse(int argc, char* argv[]) {
   Options o;
   int k;
-  while ((k = getopt(argc, argv, "c:d:p:0:n:f:t:v:b:j:x:C:")) != -1) {
+  while ((k = getopt(argc, argv, "c:d:p:0:n:f:t:v:b:j:x:C:k:")) != -1) {
     switch (k) {
       case 'c': o.circuit_file = optarg; break;
       case 'd': o.maxtime = std::atoi(optarg); break;
@@ -100,6 +101,7 @@ Options Parse(int argc, char* argv[]) {
       case 'j': o.workers = std::max(1, std::atoi(optarg)); break;
       case 'x': o.prefix = std::atoi(optarg); break;
       case 'C': o.channel = optarg; break;
+      case 'k': o.kraus_groups = std::atoi(optarg); break;
       default:
         std::fprintf(stderr, "usage: %s -c circuit [-d maxtime] [-p prob] [-0 traj0] [-n num] "
                              "[-f max_fused_size] [-t threads] [-v verbosity] [-b batch] [-j workers] [-x prefix_sharing] "
@@ -166,6 +168,8 @@ struct Counting {
   std::vector<std::complex<double>> EndExpectationBatch(unsigned max_count) const {
     return base.EndExpectationBatch(max_count);
   }
+  void RegisterOperatorGroup(const std::vector<const fp_type*>& ms, unsigned nq) const { base.RegisterOperatorGroup(ms, nq); }
+  uint64_t OperatorGroupHits() const { return base.OperatorGroupHits(); }
 #endif
   Base base;
 };
@@ -249,6 +253,7 @@ int main(int argc, char* argv[]) {
   PassCount passes;
   Clock::time_point first_start = Clock::time_point::max(), last_end = Clock::time_point::min();
   std::mutex merge;
+  uint64_t group_hits = 0;   // Kraus probabilities served by another operator's read pass (operator groups, -k 1)
   uint64_t prefix_skipped = 0, prefix_clean = 0;  // fused gates not applied thanks to the shared prefix; noiseless trajectories
   std::atomic<unsigned> ready{0};
   std::atomic<bool> failed{false};
@@ -263,6 +268,26 @@ int main(int argc, char* argv[]) {
     if (workers > 1) {  // CUDA's per-thread default stream: the workers' kernels interleave on the GPU
       simulator.base.SetStream(qsim::b200::kStreamPerThread);
       state_space.SetStream(qsim::b200::kStreamPerThread);
+    }
+#endif
+#ifndef QTRAJ_REFERENCE_CPU
+    if (opt.kraus_groups) {
+      // the K^dagger K of a channel's non-unitary operators form a group: whichever the sampling loop of
+      // lib/qtrajectory.h:344-352 asks for first, all of them come out of that one read pass
+      for (const auto& op : ncircuit.ops) {
+        const auto* ch = OpGetAlternative<Channel<fp_type>>(op);
+        if (!ch) continue;
+        std::vector<const fp_type*> ms;
+        unsigned nq = 0;
+        bool same = true;
+        for (const auto& kop : ch->kops) {
+          if (kop.unitary) continue;
+          if (!ms.empty() && kop.qubits.size() != nq) same = false;
+          nq = (unsigned) kop.qubits.size();
+          ms.push_back(kop.kd_k.data());
+        }
+        if (same && ms.size() >= 2) simulator.RegisterOperatorGroup(ms, nq);
+      }
     }
 #endif
     auto state = state_space.Create(circuit.num_qubits);
@@ -327,6 +352,7 @@ int main(int argc, char* argv[]) {
 #ifndef QTRAJ_REFERENCE_CPU
     prefix_skipped += cache.gates_skipped;
     prefix_clean += cache.clean_runs;
+    group_hits += simulator.OperatorGroupHits();
 #endif
     for (std::size_t k = 0; k < sums.size(); ++k) sums[k] += local[k];
     passes.gates += g_passes.gates;
@@ -348,12 +374,12 @@ int main(int argc, char* argv[]) {
 
   std::printf("{\"n\": %u, \"traj0\": %u, \"num\": %u, \"num_ops\": %zu, \"num_observables\": %zu, "
               "\"gate_passes\": %llu, \"expect_passes\": %llu, \"moment_calls\": %llu, \"workers\": %u, "
-              "\"prefix_gates_skipped\": %llu, \"noiseless_trajectories\": %llu, \"channel\": \"%s\", "
+              "\"prefix_gates_skipped\": %llu, \"noiseless_trajectories\": %llu, \"kraus_group_hits\": %llu, \"channel\": \"%s\", "
               "\"seconds\": %.6f, \"sums\": [",
               circuit.num_qubits, opt.traj0, opt.num, ncircuit.ops.size(), observables.size(),
               (unsigned long long) passes.gates, (unsigned long long) passes.expects,
               (unsigned long long) passes.moment_calls, workers, (unsigned long long) prefix_skipped,
-              (unsigned long long) prefix_clean, opt.channel.c_str(), seconds);
+              (unsigned long long) prefix_clean, (unsigned long long) group_hits, opt.channel.c_str(), seconds);
   for (std::size_t k = 0; k < sums.size(); ++k) {
     std::printf("%s%.9g, %.9g", k ? ", " : "", sums[k].real(), sums[k].imag());
   }

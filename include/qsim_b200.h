@@ -74,6 +74,11 @@ uint64_t qb200_launch_count(const qb200_ctx* ctx);
  * "k_gate_tile<4>", "k_gate_reg<2>", ...): bench.py labels its per-kernel roofline with it instead of
  * re-stating the dispatch rule.  Static storage; "" before the first pass. */
 const char* qb200_last_kernel_name(const qb200_ctx* ctx);
+/* Process-wide counter that advances with every library call that may have written a state (gate passes, the Set... calls, Add,
+ * Multiply, Collapse, copies into device memory, exchanges of sharded states, frees and allocations).  A cache of values
+ * derived from a state (the operator groups of include/qsim_b200/simulator_b200.h) is valid while it stands still.
+ * Writes to the raw device pointer that bypass this library are not seen. */
+uint64_t qb200_mutation_epoch(void);
 /* Persistent grids of this context are sized for `sms` SMs instead of all 148 (0 = all): used while an
  * exchange kernel of a sharded state owns the remaining SMs (csrc/sharded.cu). */
 int qb200_ctx_set_sm_limit(qb200_ctx* ctx, int sms);
@@ -195,6 +200,14 @@ int qb200_inner_product(qb200_ctx* ctx, int dtype, const void* s1, const void* s
 int qb200_real_inner_product(qb200_ctx* ctx, int dtype, const void* s1, const void* s2,
                              unsigned num_qubits, double* out);
 int qb200_norm(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits, double* out);
+/* <psi|M_i|psi> for `count` (<= 8) operators on the SAME one or two qubits in ONE read pass (csrc/expect_multi.cu):
+ * matrices = count row-major 2^G x 2^G interleaved (re, im) matrices back to back, out_re_im[2i], [2i+1].  What the
+ * Kraus-operator sampling of a non-unitary channel needs (lib/qtrajectory.h:344-352: one ExpectationValue per
+ * operator, state and qubits unchanged in between).  Arithmetic per operator as in qb200_expectation_value.
+ * QB200_ERR_UNSUPPORTED for more than 2 target qubits or more than 8 operators.  Inside a reduce batch: `count` slots. */
+int qb200_expectation_values_multi(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits,
+                                   const unsigned* qs, unsigned num_targets, const void* matrices, unsigned count,
+                                   double* out_re_im);
 /* Sample (:243-312) minus the host RNG: sorted_rs are the sorted uniform
  * [0,norm) values the caller drew (lib/util.h:67-85); out[m] = first index k
  * whose cumulative probability exceeds sorted_rs[m]; 2^n - 1 when none does

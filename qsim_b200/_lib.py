@@ -58,6 +58,8 @@ SIGNATURES = {
     "qb200_norm": (_i, [_vp, _i, _vp, _u, _pd]),
     "qb200_sample": (_i, [_vp, _i, _vp, _u, _pd, _u64, _pu64]),
     "qb200_generate_random_values": (_i, [_u64, _u, _d, _pd]),
+    "qb200_mutation_epoch": (_u64, []),
+    "qb200_expectation_values_multi": (_i, [_vp, _i, _vp, _u, _pu, _u, _vp, _u, _pd]),
     "qb200_sample_seeded": (_i, [_vp, _i, _vp, _u, _u64, _u, _d, _pu64]),
     "qb200_generate_random_values_device": (_i, [_vp, _u64, _u, _d, _pd]),
     "qb200_partial_norms_count": (_u64, [_u]),

@@ -103,6 +103,20 @@ class _Base:
     def launch_count(self) -> int:
         return int(self._lib.qb200_launch_count(self._ctx))
 
+    def ExpectationValuesSameQubits(self, qs, matrices, state: State) -> np.ndarray:
+        """<psi|M_i|psi> for up to 8 operators on the same one or two qubits in one read pass
+        (qb200_expectation_values_multi, csrc/expect_multi.cu)."""
+        qs = [int(q) for q in qs]
+        cdt = np.complex64 if self.fp_type == np.float32 else np.complex128
+        ms = np.ascontiguousarray(np.stack([np.asarray(m, dtype=cdt).reshape(1 << len(qs), 1 << len(qs)) for m in matrices]))
+        out = np.zeros(2 * len(matrices), dtype=np.float64)
+        q = (C.c_uint * len(qs))(*qs)
+        self._check(self._lib.qb200_expectation_values_multi(self._ctx, self._dt, state.get(), state.num_qubits(), q, len(qs),
+                                                             ms.ctypes.data_as(C.c_void_p), len(matrices),
+                                                             out.ctypes.data_as(C.POINTER(C.c_double))),
+                    "ExpectationValuesSameQubits")
+        return out.view(np.complex128)
+
     def last_kernel_name(self) -> str:
         """the gate / expectation kernel the dispatcher chose for this object's last pass"""
         return self._lib.qb200_last_kernel_name(self._ctx).decode()

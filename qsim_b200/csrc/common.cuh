@@ -99,6 +99,11 @@ inline int cuda_status(qb200_ctx* ctx, cudaError_t e) {
 // reach it over the interconnect, or fault); one runtime query per new pointer, remembered in the context.
 int check_state_device(qb200_ctx* ctx, const void* p);
 
+// Process-wide count of operations that may have WRITTEN a state (gate passes, element-wise maps, copies into device
+// memory, exchanges, frees): what a cache of results derived from a state is validated against
+// (qb200_mutation_epoch, include/qsim_b200/simulator_b200.h operator groups).
+void note_state_written();
+
 // Lazily grown device scratch / pinned host slot.
 int ensure_scratch(qb200_ctx* ctx, size_t bytes);
 int ensure_pinned(qb200_ctx* ctx, size_t bytes);

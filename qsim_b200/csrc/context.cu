@@ -144,6 +144,9 @@ int ensure_results(qb200_ctx* ctx, uint32_t slots) {
   return QB200_OK;
 }
 
+static std::atomic<uint64_t> g_mutation_epoch{1};
+void note_state_written() { g_mutation_epoch.fetch_add(1, std::memory_order_relaxed); }
+
 // partials[0 .. 2*blocks) -> out[2] on the host (synchronises the stream); inside a batch
 // (qb200_reduce_batch_begin) -> the next result slot, no synchronisation, `out` = NaN.
 int finish_expectation(qb200_ctx* ctx, double* partials, uint32_t blocks, double out[2]) {
@@ -160,6 +163,27 @@ int finish_expectation(qb200_ctx* ctx, double* partials, uint32_t blocks, double
   QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   out[0] = ctx->res[0];
   out[1] = ctx->res[1];
+  return QB200_OK;
+}
+
+// `count` results at once: partials[(o * blocks + b) * 2 + {0,1}] -> out[2 * o + {0,1}]; inside a batch the next
+// `count` slots.
+int finish_expectations(qb200_ctx* ctx, double* partials, uint32_t blocks, uint32_t count, double* out) {
+  const uint32_t slot = ctx->batching ? ctx->batch_count : 0;
+  int rc = ensure_results(ctx, slot + count);
+  if (rc) return rc;
+  for (uint32_t o = 0; o < count; ++o) {
+    k_sum_partials2<<<1, 256, 0, ctx->stream>>>(partials + size_t{o} * blocks * 2, blocks, ctx->res + 2 * size_t{slot + o});
+    QB_LAUNCHED(ctx);
+  }
+  if (ctx->batching) {
+    ctx->batch_count += count;
+    if (out)
+      for (uint32_t i = 0; i < 2 * count; ++i) out[i] = std::numeric_limits<double>::quiet_NaN();
+    return QB200_OK;
+  }
+  QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (uint32_t i = 0; i < 2 * count; ++i) out[i] = ctx->res[i];
   return QB200_OK;
 }
 
@@ -183,6 +207,8 @@ using namespace qb200;
 extern "C" {
 
 int qb200_abi_version(void) { return 2; }
+
+uint64_t qb200_mutation_epoch(void) { return g_mutation_epoch.load(std::memory_order_relaxed); }
 
 int qb200_device_count(int* count) {
   if (!count) return QB200_ERR_INVALID;
@@ -293,6 +319,7 @@ static int state_alloc(unsigned num_qubits, int dtype, void** state) {
   *state = nullptr;
   size_t bytes = qb200_min_size(num_qubits) * (dtype == QB200_F32 ? 4 : 8);
   if (bytes < 256) bytes = 256;
+  note_state_written();   // a fresh allocation may reuse the address of a freed state
   cudaError_t e = cudaMalloc(state, bytes);
   if (e != cudaSuccess) {
     (void) cudaGetLastError();
@@ -325,6 +352,7 @@ int qb200_ctx_set_sm_limit(qb200_ctx* ctx, int sms) {
 }
 
 int qb200_state_free(void* state) {
+  note_state_written();
   if (!state) return QB200_OK;
   return cudaFree(state) == cudaSuccess ? QB200_OK : QB200_ERR_CUDA;
 }
@@ -332,6 +360,7 @@ int qb200_state_free(void* state) {
 static size_t scalar_bytes(int dtype) { return dtype == QB200_F32 ? 4 : 8; }
 
 int qb200_copy_d2d(qb200_ctx* ctx, int dtype, const void* src, void* dst, uint64_t count) {
+  note_state_written();
   if (!ctx || !src || !dst) return QB200_ERR_INVALID;
   DeviceGuard guard(ctx);
   QB_CUDA(ctx, cudaMemcpyAsync(dst, src, count * scalar_bytes(dtype), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -340,6 +369,7 @@ int qb200_copy_d2d(qb200_ctx* ctx, int dtype, const void* src, void* dst, uint64
 }
 
 int qb200_copy_d2d_async(qb200_ctx* ctx, int dtype, const void* src, void* dst, uint64_t count) {
+  note_state_written();
   if (!ctx || !src || !dst) return QB200_ERR_INVALID;
   DeviceGuard guard(ctx);
   QB_CUDA(ctx, cudaMemcpyAsync(dst, src, count * scalar_bytes(dtype), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -355,6 +385,7 @@ int qb200_copy_d2h(qb200_ctx* ctx, int dtype, const void* src, void* host_dst, u
 }
 
 int qb200_copy_h2d(qb200_ctx* ctx, int dtype, const void* host_src, void* dst, uint64_t count) {
+  note_state_written();
   if (!ctx || !host_src || !dst) return QB200_ERR_INVALID;
   DeviceGuard guard(ctx);
   QB_CUDA(ctx, cudaMemcpyAsync(dst, host_src, count * scalar_bytes(dtype), cudaMemcpyHostToDevice, ctx->stream));

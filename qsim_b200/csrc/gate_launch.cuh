@@ -246,6 +246,7 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
   if (nq > kMaxTargets) return QB200_ERR_UNSUPPORTED;
   DeviceGuard guard(ctx);
   if (int drc = check_state_device(ctx, st)) return drc;
+  if constexpr (!EXPECT) note_state_written();
 
   const bool aligned16 = (reinterpret_cast<uintptr_t>(st) & 15) == 0;
   bool generic = ctx->tune.force_generic || (int) nq > RegLimits<FP>::kMaxG ||

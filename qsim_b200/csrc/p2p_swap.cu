@@ -114,6 +114,7 @@ int qb200_swap_global_local(qb200_ctx* ctx, int dtype, void* state, unsigned n_l
                             void* const* peer_states, unsigned k, const unsigned* local_bits,
                             unsigned my_value) {
   if (!ctx || !state || !peer_states || !local_bits || k < 1 || k > kMaxSwapBits) return QB200_ERR_INVALID;
+  note_state_written();
   if (dtype != QB200_F32 && dtype != QB200_F64) return QB200_ERR_INVALID;
   if (n_local < k + 2 || n_local > kMaxQubits || my_value >= (1u << k)) return QB200_ERR_INVALID;
   SwapGeom g{};

@@ -846,6 +846,7 @@ static void launch_push_tma(qb200_sv* sv, Shard& s, const RemapGeom& rg, size_t 
 // fits beside resident gate kernels
 static int push_launch(qb200_sv* sv, Shard& s, PushPlan& pp, cudaStream_t stream, bool slim) {
   DevScope d(s.device);
+  note_state_written();
   RemapGeom& rg = pp.rg;
   const int nb = 1 - sv->cur;
   rg.my = pick_bits(s.rank, pp.gb, pp.k);

@@ -62,6 +62,7 @@ template <typename FP, bool LOAD, typename F>
 int launch_map(qb200_ctx* ctx, FP* st, unsigned n, F f) {
   if (!ctx || !st || n > kMaxQubits || !aligned_ok<FP>(st)) return QB200_ERR_INVALID;
   DeviceGuard guard(ctx);
+  note_state_written();
   const uint64_t amps = uint64_t{1} << n;
   if (pair_ok<FP>(st, n)) {
     const uint64_t items = amps / 2;
@@ -457,6 +458,7 @@ using namespace qb200;
 extern "C" {
 
 int qb200_set_all_zeros(qb200_ctx* ctx, int dtype, void* state, unsigned n) {
+  note_state_written();
   QB_DISPATCH(dtype, set_all_zeros<FP>(ctx, (FP*) state, n), set_all_zeros<FP>(ctx, (FP*) state, n));
 }
 
@@ -479,6 +481,7 @@ int qb200_get_ampl(qb200_ctx* ctx, int dtype, const void* state, uint64_t i, dou
 }
 
 int qb200_set_ampl(qb200_ctx* ctx, int dtype, void* state, uint64_t i, double re, double im) {
+  note_state_written();
   QB_DISPATCH(dtype, set_ampl<FP>(ctx, (FP*) state, i, re, im), set_ampl<FP>(ctx, (FP*) state, i, re, im));
 }
 

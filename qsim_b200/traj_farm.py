@@ -48,6 +48,7 @@ def merge(results):
         "moment_calls": sum(r.get("moment_calls", 0) for r in results),
         "prefix_gates_skipped": sum(r.get("prefix_gates_skipped", 0) for r in results),
         "noiseless_trajectories": sum(r.get("noiseless_trajectories", 0) for r in results),
+        "kraus_group_hits": sum(r.get("kraus_group_hits", 0) for r in results),
         "algorithmic_GBps": abytes / slowest / 1e9 if slowest > 0 else float("nan"),
         "mean": [s / num for s in sums], "sums": sums,
     }

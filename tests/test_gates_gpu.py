@@ -531,3 +531,34 @@ def test_tensor_core_path_on_structured_matrices_and_sparse_states(oracle, g):
         qs = sorted(rng.choice(np.arange(n), g, replace=False).tolist())
         sim.ApplyGate(qs, random_unitary(g, it, np.complex64), st)
     assert abs(ss.Norm(st) - 1.0) < 60 * 2e-7
+
+
+@pytest.mark.parametrize("cdt", [np.complex64, np.complex128])
+def test_expectation_values_of_several_operators_in_one_pass(oracle, cdt):
+    """qb200_expectation_values_multi (csrc/expect_multi.cu): up to 8 operators on the same 1 or 2 qubits, one read
+    pass -- each value equals the oracle's ExpectationValue of that operator (lib/simulator_basic.h:286-342
+    arithmetic: products in the state's precision, sums in double), for low / high / mixed qubits, non-Hermitian
+    matrices included; more than 2 qubits or 8 operators is refused without touching the output."""
+    import qsim_b200
+    from qsim_b200 import _lib
+    rdt = np.float32 if cdt == np.complex64 else np.float64
+    ss, sim = qsim_b200.StateSpaceB200(rdt), qsim_b200.SimulatorB200(rdt)
+    n = 17
+    h = random_state(n, cdt, 77)
+    st = ss.Create(n)
+    ss.from_numpy(h, st)
+    rng = np.random.default_rng(5)
+    tol = 2e-6 if cdt == np.complex64 else 1e-13
+    for qs in ([0], [1], [4], [n - 1], [0, 1], [0, 9], [3, 4], [7, n - 1], [n - 2, n - 1]):
+        d = 1 << len(qs)
+        for count in (1, 2, 5, 8):
+            ms = [(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))).astype(cdt) for _ in range(count)]
+            got = sim.ExpectationValuesSameQubits(qs, ms, st)
+            for m, v in zip(ms, got):
+                assert abs(v - oracle.expectation_value(h, qs, m)) < tol * d * 4, (qs, count)
+    assert np.array_equal(ss.to_numpy(st), h)   # read-only
+    with pytest.raises(qsim_b200.QB200Error) as e:
+        sim.ExpectationValuesSameQubits([0, 1, 2], [np.eye(8)], st)
+    assert e.value.status == _lib.ERR_UNSUPPORTED
+    with pytest.raises(qsim_b200.QB200Error):
+        sim.ExpectationValuesSameQubits([0], [np.eye(2)] * 9, st)

@@ -151,3 +151,12 @@ def test_amplitude_damping_trajectories_match_reference_cpu(circuit_file):
     assert np.abs(np.array(got["sums"]) - np.array(ref["sums"])).max() < 6 * 5e-5
     clean = traj_farm.run_farm(circuit_file, 0, 1, gpus=1, p=0.0, binary=REF, device_ids=[None])
     assert np.abs(np.array(ref["sums"]) / 6 - np.array(clean["sums"])).max() > 1e-3   # the damping matters
+    # operator groups (default, -k 1): when the sampling loop gets as far as the second Kraus operator, its probability
+    # comes out of the pass that evaluated the first (qb200_expectation_values_multi).  Strong damping so that it does.
+    strong = [traj_farm.run_farm(circuit_file, 0, 6, gpus=1, p=0.3, extra_args=args + ("-k", k)) for k in ("1", "0")]
+    sref = traj_farm.run_farm(circuit_file, 0, 6, gpus=1, p=0.3, binary=REF, device_ids=[None], extra_args=args)
+    assert strong[0]["kraus_group_hits"] > 0 and strong[1]["kraus_group_hits"] == 0
+    assert strong[0]["expect_passes"] == strong[1]["expect_passes"]   # same sampling path: same ExpectationValue calls
+    assert strong[0]["gate_passes"] == strong[1]["gate_passes"] == sref["gate_passes"]
+    for got in strong:
+        assert np.abs(np.array(got["sums"]) - np.array(sref["sums"])).max() < 6 * 5e-5
