@@ -574,11 +574,12 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
     for (int m = 0; m < MT; ++m) {
       const uint32_t ahi = tmem_base + b * BUFC + m * 3 * KF, alo = ahi + KF, d = ahi + 2 * KF;
       uint32_t acc = 0;
-      // smallest terms first: A_hi (c W_hi), A_lo W_hi, A_hi W_lo, A_hi W_hi
+      // smallest terms first: A_lo W_hi, A_hi W_lo, A_hi W_hi (the accumulation-bias compensation is an FMA in
+      // store_mine, not a fourth MMA term: a quarter less tensor work per tile)
 #pragma unroll
-      for (int term = COMP ? 0 : 1; term < 4; ++term) {
+      for (int term = 1; term < 4; ++term) {
         const uint32_t ab = term == 1 ? alo : ahi;
-        const uint32_t bb = term == 0 ? bc_s : term == 2 ? blo_s : bhi_s;
+        const uint32_t bb = term == 2 ? blo_s : bhi_s;
 #pragma unroll
         for (int k = 0; k < KF / 8; ++k) {
           const uint64_t bd = tc::smem_desc_sw128(bb + (k >> 2) * S::B_ATOM + (k & 3) * 32);
@@ -595,7 +596,13 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
     tc::fence_after();
   };
 
-  auto store_mine = [&](unsigned char* p, const uint32_t (&v)[N]) {
+  auto store_mine = [&](unsigned char* p, uint32_t (&v)[N]) {
+    if constexpr (COMP) {
+      // the tensor core truncates its fp32 accumulation: a pass shrinks the state by ~(1 - tc_bias); v + c v with one
+      // rounding puts the mean back
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), tc_bias<G>(), __uint_as_float(v[j])));
+    }
 #pragma unroll
     for (int j = 0; j < HN; j += (PAIR ? 2 : 1)) {
       if constexpr (PAIR) {
@@ -732,7 +739,7 @@ k_gate_tca(float* __restrict__ st, const __grid_constant__ Geom g,
 // not fit the kernel parameter space).  One operand/accumulator buffer, one tile of prefetch.
 // ---------------------------------------------------------------------------------------------
 template <int G>
-constexpr size_t tcx_smem_bytes() { return 1024 + 3 * TcShape<G>::B_TILE; }
+constexpr size_t tcx_smem_bytes() { return 1024 + 2 * TcShape<G>::B_TILE; }   // W_hi, W_lo
 
 template <int G, bool PAIR, bool EXPECT>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -755,7 +762,7 @@ k_gate_tcx(float* __restrict__ st, const __grid_constant__ Geom g, const float* 
   const uint32_t raw_s = smem_u32(tc_raw);
   const uint32_t base_s = (raw_s + 1023u) & ~1023u;
   unsigned char* const base_p = tc_raw + (base_s - raw_s);
-  const uint32_t bhi_s = base_s, blo_s = base_s + S::B_TILE, bc_s = base_s + 2 * S::B_TILE;
+  const uint32_t bhi_s = base_s, blo_s = base_s + S::B_TILE;
 
   for (uint32_t idx = t; idx < (uint32_t) (KF * KF); idx += kTcThreads) {
     const uint32_t n = idx / KF, k = idx % KF;
@@ -766,7 +773,6 @@ k_gate_tcx(float* __restrict__ st, const __grid_constant__ Geom g, const float* 
     const uint32_t off = (k >> 5) * S::B_ATOM + sw128_off(n, (k & 31) >> 2) + (k & 3) * 4;
     *reinterpret_cast<float*>(base_p + off) = hi;
     *reinterpret_cast<float*>(base_p + S::B_TILE + off) = w - hi;
-    *reinterpret_cast<float*>(base_p + 2 * S::B_TILE + off) = comp * hi;
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
@@ -837,14 +843,16 @@ k_gate_tcx(float* __restrict__ st, const __grid_constant__ Geom g, const float* 
     tc::tmem_st_wait();
   };
 
-  auto issue_mmas = [&]() {
+  // accumulator buffer b (gates: two of them, so that tile i's MMAs run while tile i-1 is read out and stored; the
+  // allocation is the power of two above 3 KF = 4 KF columns anyway)
+  auto issue_mmas = [&](uint32_t b) {
     tc::fence_after();
-    const uint32_t ahi = tmem_base, alo = ahi + KF, d = ahi + 2 * KF;
+    const uint32_t ahi = tmem_base, alo = ahi + KF, d = ahi + 2 * KF + b * KF;
     uint32_t acc = 0;
 #pragma unroll
-    for (int term = EXPECT ? 1 : 0; term < 4; ++term) {
+    for (int term = 1; term < 4; ++term) {   // A_lo W_hi + A_hi W_lo + A_hi W_hi
       const uint32_t ab = term == 1 ? alo : ahi;
-      const uint32_t bb = term == 0 ? bc_s : term == 2 ? blo_s : bhi_s;
+      const uint32_t bb = term == 2 ? blo_s : bhi_s;
 #pragma unroll 4
       for (int k = 0; k < KF / 8; ++k) {
         const uint64_t bd = tc::smem_desc_sw128(bb + (k >> 2) * S::B_ATOM + (k & 3) * 32);
@@ -857,11 +865,11 @@ k_gate_tcx(float* __restrict__ st, const __grid_constant__ Geom g, const float* 
 
   double ere = 0, eim = 0;
   // tile it-1 is complete in TMEM: write it back (gate) or fold <x|D> into the accumulators (expectation)
-  auto epilogue = [&](unsigned char* p) {
+  auto epilogue = [&](unsigned char* p, uint32_t b) {
 #pragma unroll
     for (int pc = 0; pc < NPIECE; ++pc) {
       uint32_t v[PIECE];
-      tc::tmem_ld(tmem_mine + 2 * KF + pc * PIECE, v);
+      tc::tmem_ld(tmem_mine + 2 * KF + b * KF + pc * PIECE, v);
       if constexpr (EXPECT) {
         uint32_t xh[PIECE], xl[PIECE];
         tc::tmem_ld(tmem_mine + pc * PIECE, xh);
@@ -875,6 +883,11 @@ k_gate_tcx(float* __restrict__ st, const __grid_constant__ Geom g, const float* 
           eim += xr * im - xi * re;
         }
       } else {
+        // accumulation-bias compensation (tc_bias): the tensor core truncates its fp32 accumulation, a pass
+        // shrinks the state by a factor ~(1 - comp); v + comp * v, one rounding, puts the mean back.  (A fourth
+        // MMA A_hi (comp W_hi) did the same at 25 % more tensor time and a third 64 KB W tile.)
+#pragma unroll
+        for (int j = 0; j < PIECE; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), comp, __uint_as_float(v[j])));
 #pragma unroll
         for (int j = 0; j < PIECE / 2; j += (PAIR ? 2 : 1)) {
           const int a = pc * (PIECE / 2) + j;  // amplitude within the half row
@@ -894,10 +907,18 @@ k_gate_tcx(float* __restrict__ st, const __grid_constant__ Geom g, const float* 
   if (tile < ntiles) { p_cur = tile_ptr(tile); load_mine(p_cur, cur); }
   uint32_t it = 0;
   for (; tile < ntiles; tile += stride, ++it) {
-    if (it > 0) {
+    if constexpr (EXPECT) {
+      // one accumulator buffer: the epilogue re-reads x from the A columns, which the next split overwrites
+      if (it > 0) {
+        tc::mbar_wait(smem_u32(&mbar), (it - 1) & 1);
+        tc::fence_after();
+        epilogue(p_prev, 0);
+      }
+    } else if (it > 0) {
+      // tile it-1's MMAs are complete: the A columns are free, D[(it-1) & 1] is ready -- read out BELOW, after this
+      // tile's MMAs have been issued into the other accumulator buffer
       tc::mbar_wait(smem_u32(&mbar), (it - 1) & 1);
       tc::fence_after();
-      epilogue(p_prev);
     }
     split_to_tmem(cur);
     if (tile + stride < ntiles) { p_nxt = tile_ptr(tile + stride); load_mine(p_nxt, nxt); }
@@ -905,8 +926,11 @@ k_gate_tcx(float* __restrict__ st, const __grid_constant__ Geom g, const float* 
     tc::mbar_arrive(smem_u32(&full_bar));
     if (warp == 0) {
       tc::mbar_wait(smem_u32(&full_bar), it & 1);
-      if (tc::elect_one()) issue_mmas();
+      if (tc::elect_one()) issue_mmas(EXPECT ? 0u : (it & 1u));
       __syncwarp();
+    }
+    if constexpr (!EXPECT) {
+      if (it > 0) epilogue(p_prev, (it - 1) & 1);   // overlaps the MMAs just issued
     }
     p_prev = p_cur;
     p_cur = p_nxt;
@@ -916,7 +940,7 @@ k_gate_tcx(float* __restrict__ st, const __grid_constant__ Geom g, const float* 
   if (it > 0) {
     tc::mbar_wait(smem_u32(&mbar), (it - 1) & 1);
     tc::fence_after();
-    epilogue(p_prev);
+    epilogue(p_prev, EXPECT ? 0u : ((it - 1) & 1u));
   }
   tc::fence_before();
   __syncthreads();
