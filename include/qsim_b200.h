@@ -320,6 +320,7 @@ typedef struct {
   uint64_t overlapped_swaps;     /* exchanges that ran chunk by chunk beside the last gate passes of their epoch ... */
   uint64_t overlapped_gate_passes;   /* ... how many gate passes those were ... */
   double overlap_ms;             /* ... and the device time of those pipelines (gates + exchange; not in exchange_ms) */
+  uint64_t copy_engine_swaps;    /* exchanges moved by the copy engines (pitched 3-D copies) instead of a push kernel */
 } qb200_sv_stats;
 
 int qb200_sv_create(const int* devices, unsigned num_shards, unsigned num_qubits, int dtype, qb200_sv** sv);

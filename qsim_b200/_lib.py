@@ -92,7 +92,8 @@ class SvStats(C.Structure):
     """qb200_sv_stats"""
     _fields_ = [("swaps", _u64), ("local_swap_passes", _u64), ("gate_passes", _u64),
                 ("bytes_sent_per_shard", _d), ("exchange_ms", _d), ("barrier_wait_ms", _d),
-                ("overlapped_swaps", _u64), ("overlapped_gate_passes", _u64), ("overlap_ms", _d)]
+                ("overlapped_swaps", _u64), ("overlapped_gate_passes", _u64), ("overlap_ms", _d),
+                ("copy_engine_swaps", _u64)]
 
 
 SIGNATURES.update({

@@ -355,6 +355,7 @@ struct SvStats {
   uint64_t overlapped_swaps = 0;     // exchanges that ran chunk by chunk beside the last gates of their epoch
   uint64_t overlapped_gate_passes = 0;   // ... and how many gate passes those were
   double overlap_ms = 0;             // device time of those pipelines (gates + exchange), not part of exchange_ms
+  uint64_t ce_swaps = 0;             // exchanges moved by the copy engines (ce_push)
 };
 
 }  // namespace qb200
@@ -382,7 +383,9 @@ struct qb200_sv {
   int barrier_flags = 0;                 // 1: flag kernels (always in mp mode); 0: events
   int swap_mode = -1;                    // -1 auto (out of place when the second buffer fits), 0 in place, 1 out of place
   int reorder = 1;
-  int push_kernel = 1;                   // 1: bulk-copy engine (k_remap_push_tma, default); 0: st.global from registers
+  int push_kernel = 1;                   // 1: bulk-copy engine (k_remap_push_tma, default); 0: st.global from registers;
+                                         // 2: the copy engines (pitched cudaMemcpy3DAsync) when the victims sit at bit 12
+                                         //    or above, else 1
   int push_ctas_per_sm = 0;              // 0 = default of the chosen kernel
   int overlap_ctas_per_sm = 0;           // CTAs per SM of the slim push kernel that runs beside gates (0 = 1)
   int overlap_smem_kb = 0;               // ... and its shared memory per CTA (0 = 16 KB)
@@ -391,6 +394,7 @@ struct qb200_sv {
                                          // (off by default: measured no gain on B200, profiles/r02_overlap_trace.txt)
   int overlap_chunks_log2 = 2;           // 2^this chunks per shard
   int overlap_max_gates = 6;             // gate passes pipelined against one exchange (enough to cover it, see run_overlapped)
+  int overlap_ce = 1;                    // overlapped exchanges go through the copy engines when the layout allows
   int overlap_trace = 0;                 // 1: print a device timeline of the next overlapped exchange (first local shard) to stderr
   int overlap_occ_reduce = 0;            // resident gate CTAs per SM given up while the slim push kernel runs beside them
   SvStats stats;
@@ -880,6 +884,113 @@ static int push_launch(qb200_sv* sv, Shard& s, PushPlan& pp, cudaStream_t stream
   return QB200_OK;
 }
 
+// ---- the same exchange on the COPY ENGINES ----------------------------------------------------------------------
+// With every victim bit at or above bit 12 the amplitudes that go to one destination form runs of >= 32 KB, and the
+// (source, destination) address pattern of a whole shard -- or of one chunk of it -- is a pitched 3-D box: the free
+// index bits fall into runs between the pinned bits (victims: the destination's value; chunk bits: the chunk's),
+// run 0 is the contiguous row, runs 1 and 2 are the box's height and depth (cudaMemcpy3DAsync), anything above is a
+// short host loop.  The destination has the same runs at the packed positions (victim bits squeezed out).  No SM, no
+// shared memory, no L1 carveout: the gate kernels that run beside an overlapped exchange keep the SMs to themselves
+// (the SM-driven slim kernel time-shares them, profiles/r02_overlap_trace.txt).
+constexpr unsigned kCeMinBit = 12;
+constexpr unsigned kCeMaxLoop = 64;
+
+struct CeRun { unsigned start, len; };
+
+static bool ce_runs(const qb200_sv* sv, const PushPlan& pp, const unsigned* chunk_bits, unsigned nchunk,
+                    std::vector<CeRun>* runs) {
+  std::vector<unsigned> sp(pp.rg.lbits, pp.rg.lbits + pp.k);
+  for (unsigned j = 0; j < pp.k; ++j)
+    if (sp[j] < kCeMinBit) return false;
+  for (unsigned j = 0; j < nchunk; ++j) sp.push_back(chunk_bits[j]);
+  std::sort(sp.begin(), sp.end());
+  runs->clear();
+  unsigned lo = 0;
+  for (unsigned b : sp) {
+    if (b > lo) runs->push_back({lo, b - lo});
+    lo = b + 1;
+  }
+  if (sv->nl > lo) runs->push_back({lo, sv->nl - lo});
+  if (runs->empty() || (*runs)[0].start != 0) return false;
+  const size_t ab = 2 * scalar_size(sv->dtype);
+  // runs that go into the pitched box: at most two after the row, pitches below 2 GiB; the rest is looped over
+  uint64_t loops = 1;
+  for (size_t r = 1; r < runs->size(); ++r) {
+    const bool boxed = r <= 2 && ((uint64_t{1} << (*runs)[r].start) * ab) < (uint64_t{1} << 31);
+    if (!boxed) loops <<= (*runs)[r].len;
+  }
+  return loops <= kCeMaxLoop;
+}
+
+// one shard's amplitudes (all, or the chunk whose bits chunk_bits[] carry cval) to their places in the new layout
+static int ce_push(qb200_sv* sv, Shard& s, const PushPlan& pp, const unsigned* chunk_bits, unsigned nchunk,
+                   unsigned cval, cudaStream_t stream) {
+  DevScope d(s.device);
+  note_state_written();
+  std::vector<CeRun> runs;
+  if (!ce_runs(sv, pp, chunk_bits, nchunk, &runs)) return QB200_ERR_UNSUPPORTED;
+  const size_t ab = 2 * scalar_size(sv->dtype);
+  const int nb = 1 - sv->cur;
+  const unsigned k = pp.k, my = pick_bits(s.rank, pp.gb, k);
+  auto dpos = [&](unsigned bit) {   // position of a non-victim source bit in the destination index
+    unsigned below = 0;
+    for (unsigned j = 0; j < k; ++j) below += pp.rg.lbits[j] < bit;
+    return bit - below;
+  };
+  uint64_t src_fixed = 0, dst_fixed = uint64_t{my} << (sv->nl - k);
+  for (unsigned j = 0; j < nchunk; ++j) {
+    src_fixed |= uint64_t{(cval >> j) & 1u} << chunk_bits[j];
+    dst_fixed |= uint64_t{(cval >> j) & 1u} << dpos(chunk_bits[j]);
+  }
+  std::vector<CeRun> box, loop;
+  for (size_t r = 1; r < runs.size(); ++r) {
+    const bool boxed = r <= 2 && ((uint64_t{1} << runs[r].start) * ab) < (uint64_t{1} << 31);
+    (boxed ? box : loop).push_back(runs[r]);
+  }
+  uint64_t nloop = 1;
+  for (const auto& r : loop) nloop <<= r.len;
+  const size_t width = (size_t{1} << runs[0].len) * ab;
+  for (unsigned v = 0; v < (1u << k); ++v) {
+    uint64_t src_v = src_fixed;
+    for (unsigned j = 0; j < k; ++j) src_v |= uint64_t{(v >> j) & 1u} << pp.rg.lbits[j];
+    char* const dst_buf = (char*) sv->peer_buf[nb][with_bits(s.rank, pp.gb, k, v)];
+    const char* const src_buf = (const char*) s.buf[sv->cur];
+    for (uint64_t it = 0; it < nloop; ++it) {
+      uint64_t so = src_v, dof = dst_fixed, rest = it;
+      for (const auto& r : loop) {
+        const uint64_t val = rest & ((uint64_t{1} << r.len) - 1);
+        rest >>= r.len;
+        so |= val << r.start;
+        dof |= val << dpos(r.start);
+      }
+      cudaError_t e;
+      if (box.empty()) {
+        e = cudaMemcpyAsync(dst_buf + dof * ab, src_buf + so * ab, width, cudaMemcpyDefault, stream);
+      } else {
+        const size_t spitch = (size_t{1} << box[0].start) * ab, dpitch = (size_t{1} << dpos(box[0].start)) * ab;
+        const size_t height = size_t{1} << box[0].len;
+        if (box.size() == 1) {
+          e = cudaMemcpy2DAsync(dst_buf + dof * ab, dpitch, src_buf + so * ab, spitch, width, height, cudaMemcpyDefault, stream);
+        } else {
+          cudaMemcpy3DParms pm{};
+          const size_t sslice = (size_t{1} << box[1].start) * ab, dslice = (size_t{1} << dpos(box[1].start)) * ab;
+          pm.srcPtr = make_cudaPitchedPtr((void*) (src_buf + so * ab), spitch, spitch, sslice / spitch);
+          pm.dstPtr = make_cudaPitchedPtr((void*) (dst_buf + dof * ab), dpitch, dpitch, dslice / dpitch);
+          pm.extent = make_cudaExtent(width, height, size_t{1} << box[1].len);
+          pm.kind = cudaMemcpyDefault;
+          e = cudaMemcpy3DAsync(&pm, stream);
+        }
+      }
+      if (e != cudaSuccess) {
+        sv->last_error = (int) e;
+        (void) cudaGetLastError();
+        return QB200_ERR_CUDA;
+      }
+    }
+  }
+  return QB200_OK;
+}
+
 // after the trailing barrier: the spare buffers hold the state; new qubit map
 static void push_finish(qb200_sv* sv, const PushPlan& pp) {
   sv->cur = 1 - sv->cur;
@@ -938,11 +1049,17 @@ static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* in
   if (prc == QB200_OK) {
     timing_mark(sv, 0);
     timing_mark(sv, 1);  // no leading barrier: the spare buffers are free (see ensure_alt)
-    for (auto& s : sv->sh) SV_TRY(push_launch(sv, s, pp, s.stream, false));
+    std::vector<CeRun> runs;
+    const bool ce = sv->push_kernel == 2 && ce_runs(sv, pp, nullptr, 0, &runs);
+    for (auto& s : sv->sh) {
+      if (ce) SV_TRY(ce_push(sv, s, pp, nullptr, 0, 0, s.stream));
+      else SV_TRY(push_launch(sv, s, pp, s.stream, false));
+    }
     timing_mark(sv, 2);  // (recorded after the launches of every local shard; the first shard's stream only holds its own)
     SV_TRY(barrier(sv));
     timing_mark(sv, 3);
     push_finish(sv, pp);
+    sv->stats.ce_swaps += ce;
     return QB200_OK;
   } else {
     // in place (k_p2p_swap): local bit <-> rank bit; low victims are lifted first, at most 3 bits per pass
@@ -1073,6 +1190,8 @@ static int run_overlapped(qb200_sv* sv, const qb200_gate* gates, const std::vect
   sv->ev_overlapped[sv->ev_used] = 1;
   for (auto& s : sv->sh) s.ctx->occ_reduce = sv->overlap_occ_reduce;
   int rc = QB200_OK;
+  std::vector<CeRun> ce_probe;
+  const bool ce = sv->overlap_ce != 0 && ce_runs(sv, pp, spec.chunk_bits, c, &ce_probe);
   // debugging aid: CUDA events around every chunk's gates (main stream) and push (second stream) of the first shard
   std::vector<cudaEvent_t> tr;
   const bool trace = sv->overlap_trace != 0;
@@ -1104,7 +1223,7 @@ static int run_overlapped(qb200_sv* sv, const qb200_gate* gates, const std::vect
         break;
       }
       if (&s == &sv->sh[0]) mark(s.stream2);
-      rc = push_launch(sv, s, pp, s.stream2, true);
+      rc = ce ? ce_push(sv, s, pp, spec.chunk_bits, c, v, s.stream2) : push_launch(sv, s, pp, s.stream2, true);
       if (&s == &sv->sh[0]) mark(s.stream2);
     }
   }
@@ -1131,6 +1250,7 @@ static int run_overlapped(qb200_sv* sv, const qb200_gate* gates, const std::vect
   timing_mark(sv, 3);
   push_finish(sv, pp);
   ++sv->stats.overlapped_swaps;
+  sv->stats.ce_swaps += ce;
   sv->stats.overlapped_gate_passes += spec.swap - spec.start;
   return QB200_OK;
 }
@@ -1330,6 +1450,7 @@ int qb200_sv_set_option(qb200_sv* sv, const char* key, int value) {
   else if (!std::strcmp(key, "overlap_max_gates")) sv->overlap_max_gates = value;
   else if (!std::strcmp(key, "overlap_occ_reduce")) sv->overlap_occ_reduce = value;
   else if (!std::strcmp(key, "overlap_trace")) sv->overlap_trace = value;
+  else if (!std::strcmp(key, "overlap_ce")) sv->overlap_ce = value;
   else if (!std::strcmp(key, "overlap_ctas_per_sm")) sv->overlap_ctas_per_sm = value;
   else if (!std::strcmp(key, "overlap_smem_kb")) sv->overlap_smem_kb = value;
   else if (!std::strcmp(key, "overlap_tile_bits")) sv->overlap_tile_bits = value;
@@ -1363,6 +1484,7 @@ int qb200_sv_get_stats(qb200_sv* sv, qb200_sv_stats* out) {
   out->overlapped_swaps = sv->stats.overlapped_swaps;
   out->overlapped_gate_passes = sv->stats.overlapped_gate_passes;
   out->overlap_ms = sv->stats.overlap_ms;
+  out->copy_engine_swaps = sv->stats.ce_swaps;
   return QB200_OK;
 }
 

@@ -90,6 +90,37 @@ def test_exchange_is_an_exact_index_permutation(shards, swap_mode, barrier_flags
     st.close()
 
 
+@pytest.mark.parametrize("shards,dtype", [(2, np.float32), (4, np.float32), (8, np.float32), (4, np.float64)])
+def test_copy_engine_exchange_is_the_same_permutation(shards, dtype):
+    """push_kernel = 2 (csrc/sharded.cu ce_push): with the victims at bit 12 or above the exchange is a set of pitched
+    2-D / 3-D copies on the copy engines -- bit for bit the permutation the qubit map announces, for victims that are
+    adjacent, apart, at the top, and mixed with one below bit 12 (falls back to the push kernel)."""
+    g = shards.bit_length() - 1
+    nl = 17
+    n = nl + g
+    cd = np.complex64 if dtype == np.float32 else np.complex128
+    want = random_state(n, cd, 9)
+    st = make(shards, n, dtype, swap_mode=1, push_kernel=2)
+    st.from_numpy(want)
+    rng = np.random.default_rng(shards)
+    cases = [[12], [nl - 1], [13, 14, 15][:g], [nl - 1, nl - 3, 12][:g], [14], [3, nl - 1][:g]]
+    expect_ce = 0
+    for victims_phys in cases:
+        pos = st.qubit_map()
+        at = {p: q for q, p in enumerate(pos)}
+        victims = [at[p] for p in victims_phys]
+        glob = [at[nl + t] for t in range(g)]
+        incoming = [int(q) for q in rng.permutation(glob)[:len(victims)]]
+        st.Swap(victims, incoming)
+        expect_ce += min(victims_phys) >= 12
+        pos = st.qubit_map()
+        got = logical_from_physical(raw_shards(st), pos)
+        assert np.array_equal(got, want), f"victims at {victims_phys}"
+    stats = st.stats()
+    assert stats["swaps"] == len(cases) and stats["copy_engine_swaps"] == expect_ce
+    st.close()
+
+
 def random_ops(n, count, seed, max_targets):
     from qsim_b200.trace import TraceOp
     rs = np.random.RandomState(seed)
@@ -163,7 +194,7 @@ def test_exchange_overlapped_with_the_last_gates_of_the_epoch(oracle, shards, ch
     want = oracle_run(oracle, n, ops, cd)
     states = []
     for overlap in (1, 0):
-        st = make(shards, n, dtype, overlap=overlap, overlap_chunks_log2=chunks_log2)
+        st = make(shards, n, dtype, overlap=overlap, overlap_chunks_log2=chunks_log2, overlap_ce=shards != 8)
         st.SetStateZero()
         st.Run(ops)
         stats = st.stats()
