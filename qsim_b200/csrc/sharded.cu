@@ -893,9 +893,20 @@ static int push_launch(qb200_sv* sv, Shard& s, PushPlan& pp, cudaStream_t stream
 // shared memory, no L1 carveout: the gate kernels that run beside an overlapped exchange keep the SMs to themselves
 // (the SM-driven slim kernel time-shares them, profiles/r02_overlap_trace.txt).
 constexpr unsigned kCeMinBit = 12;
-constexpr unsigned kCeMaxLoop = 64;
+constexpr unsigned kCeMaxLoop = 256;
 
 struct CeRun { unsigned start, len; };
+
+// index of the run that becomes the height of the 2-D copies (-1: none qualifies)
+static int ce_box_run(const qb200_sv* sv, const std::vector<CeRun>& runs) {
+  const size_t ab = 2 * scalar_size(sv->dtype);
+  int best = -1;
+  for (size_t r = 1; r < runs.size(); ++r) {
+    if (((uint64_t{1} << runs[r].start) * ab) >= (uint64_t{1} << 31)) continue;
+    if (best < 0 || runs[r].len > runs[best].len) best = (int) r;
+  }
+  return best;
+}
 
 static bool ce_runs(const qb200_sv* sv, const PushPlan& pp, const unsigned* chunk_bits, unsigned nchunk,
                     std::vector<CeRun>* runs) {
@@ -912,13 +923,12 @@ static bool ce_runs(const qb200_sv* sv, const PushPlan& pp, const unsigned* chun
   }
   if (sv->nl > lo) runs->push_back({lo, sv->nl - lo});
   if (runs->empty() || (*runs)[0].start != 0) return false;
-  const size_t ab = 2 * scalar_size(sv->dtype);
-  // runs that go into the pitched box: at most two after the row, pitches below 2 GiB; the rest is looped over
+  // the longest run above the row becomes the height of a pitched 2-D copy (pitch below 2 GiB), the others are looped
+  // over on the host (3-D copies of linear memory do not run at copy-engine speed: 165 GB/s measured)
+  const int boxed = ce_box_run(sv, *runs);
   uint64_t loops = 1;
-  for (size_t r = 1; r < runs->size(); ++r) {
-    const bool boxed = r <= 2 && ((uint64_t{1} << (*runs)[r].start) * ab) < (uint64_t{1} << 31);
-    if (!boxed) loops <<= (*runs)[r].len;
-  }
+  for (size_t r = 1; r < runs->size(); ++r)
+    if ((int) r != boxed) loops <<= (*runs)[r].len;
   return loops <= kCeMaxLoop;
 }
 
@@ -943,10 +953,8 @@ static int ce_push(qb200_sv* sv, Shard& s, const PushPlan& pp, const unsigned* c
     dst_fixed |= uint64_t{(cval >> j) & 1u} << dpos(chunk_bits[j]);
   }
   std::vector<CeRun> box, loop;
-  for (size_t r = 1; r < runs.size(); ++r) {
-    const bool boxed = r <= 2 && ((uint64_t{1} << runs[r].start) * ab) < (uint64_t{1} << 31);
-    (boxed ? box : loop).push_back(runs[r]);
-  }
+  const int boxed = ce_box_run(sv, runs);
+  for (size_t r = 1; r < runs.size(); ++r) ((int) r == boxed ? box : loop).push_back(runs[r]);
   uint64_t nloop = 1;
   for (const auto& r : loop) nloop <<= r.len;
   const size_t width = (size_t{1} << runs[0].len) * ab;
@@ -969,17 +977,7 @@ static int ce_push(qb200_sv* sv, Shard& s, const PushPlan& pp, const unsigned* c
       } else {
         const size_t spitch = (size_t{1} << box[0].start) * ab, dpitch = (size_t{1} << dpos(box[0].start)) * ab;
         const size_t height = size_t{1} << box[0].len;
-        if (box.size() == 1) {
-          e = cudaMemcpy2DAsync(dst_buf + dof * ab, dpitch, src_buf + so * ab, spitch, width, height, cudaMemcpyDefault, stream);
-        } else {
-          cudaMemcpy3DParms pm{};
-          const size_t sslice = (size_t{1} << box[1].start) * ab, dslice = (size_t{1} << dpos(box[1].start)) * ab;
-          pm.srcPtr = make_cudaPitchedPtr((void*) (src_buf + so * ab), spitch, spitch, sslice / spitch);
-          pm.dstPtr = make_cudaPitchedPtr((void*) (dst_buf + dof * ab), dpitch, dpitch, dslice / dpitch);
-          pm.extent = make_cudaExtent(width, height, size_t{1} << box[1].len);
-          pm.kind = cudaMemcpyDefault;
-          e = cudaMemcpy3DAsync(&pm, stream);
-        }
+        e = cudaMemcpy2DAsync(dst_buf + dof * ab, dpitch, src_buf + so * ab, spitch, width, height, cudaMemcpyDefault, stream);
       }
       if (e != cudaSuccess) {
         sv->last_error = (int) e;
@@ -1192,6 +1190,15 @@ static int run_overlapped(qb200_sv* sv, const qb200_gate* gates, const std::vect
   int rc = QB200_OK;
   std::vector<CeRun> ce_probe;
   const bool ce = sv->overlap_ce != 0 && ce_runs(sv, pp, spec.chunk_bits, c, &ce_probe);
+  if (sv->overlap_trace) {
+    fprintf(stderr, "overlap trace: victims at bits");
+    for (unsigned j = 0; j < rg.k; ++j) fprintf(stderr, " %u", rg.lbits[j]);
+    fprintf(stderr, ", chunk bits");
+    for (unsigned j = 0; j < c; ++j) fprintf(stderr, " %u", spec.chunk_bits[j]);
+    fprintf(stderr, ", copy engines %d, runs", (int) ce);
+    for (const auto& r : ce_probe) fprintf(stderr, " [%u,+%u)", r.start, r.len);
+    fprintf(stderr, "\n");
+  }
   // debugging aid: CUDA events around every chunk's gates (main stream) and push (second stream) of the first shard
   std::vector<cudaEvent_t> tr;
   const bool trace = sv->overlap_trace != 0;

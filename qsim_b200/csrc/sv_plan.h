@@ -157,7 +157,10 @@ class SwapPlanner {
       const double ra = a.ex.size() / (1.0 - 1.0 / (1u << a.k)), rb = b.ex.size() / (1.0 - 1.0 / (1u << b.k));
       if (ra != rb) return ra > rb;
       if (a.ex.size() != b.ex.size()) return a.ex.size() > b.ex.size();
-      return a.k < b.k;
+      if (a.k != b.k) return a.k < b.k;
+      // equal otherwise: prefer HIGH qubits as the new global ones -- victims on high index bits travel as long
+      // contiguous runs (no sorting inside the push kernel's tiles; the copy engines can take them)
+      return a.set > b.set;
     });
     if (v->size() > beam) v->resize(beam);
   }
