@@ -221,6 +221,8 @@ int qb200_generate_random_values(uint64_t num_samples, unsigned seed, double max
  * MT19937 + libstdc++'s uniform_real_distribution<double> arithmetic + radix sort, bit-identical to the host helper
  * (csrc/sample_rng.cu).  qb200_sample_seeded = Sample(state, num_samples, seed) with `norm` = the caller's Norm(state):
  * no host random numbers, no host sort, no host->device copy; same indices as qb200_sample on the host values.
+ * norm < 0: the values are drawn in [0, total of the sampler's own chunk sums) -- Norm(state) up to the summation order,
+ * without the separate Norm pass (two reads of the state per call instead of three).
  * qb200_generate_random_values_device copies the sorted values to host memory `out` (tests). */
 int qb200_sample_seeded(qb200_ctx* ctx, int dtype, const void* state, unsigned num_qubits, uint64_t num_samples,
                         unsigned seed, double norm, uint64_t* out);

@@ -116,14 +116,15 @@ class StateSpaceB200 : public StateSpace<StateSpaceB200<FP>, VectorSpaceB200, FP
   std::vector<uint64_t> Sample(const State& state, uint64_t num_samples, unsigned seed) const {
     std::vector<uint64_t> bitstrings;
     if (num_samples > 0) {
-      double norm = Norm(state);
       bitstrings.resize(num_samples, 0);
       if (std::is_same<DistrRealType, double>::value) {
         // the reference's TODO (lib/statespace_cuda.h:292): the values GenerateRandomValues<double> would draw on
-        // the host are drawn and sorted on the device, bit for bit (csrc/sample_rng.cu)
+        // the host are drawn and sorted on the device, bit for bit (csrc/sample_rng.cu); norm = -1: the upper bound
+        // is the total of the sampler's own partial sums (Norm(state) without a third pass over the state)
         QB200_CHECK(this->ctx(), qb200_sample_seeded(this->ctx(), kDT, state.get(), state.num_qubits(), num_samples,
-                                                     seed, norm, bitstrings.data()));
+                                                     seed, -1.0, bitstrings.data()));
       } else {
+        double norm = Norm(state);
         // any other distribution type: host RNG exactly as the reference draws it (lib/statespace_cuda.h:293)
         auto rs = GenerateRandomValues<DistrRealType>(num_samples, seed, norm);
         std::vector<double> rsd(rs.begin(), rs.begin() + num_samples);

@@ -275,17 +275,20 @@ class StateSpaceB200(_Base):
                     "GenerateRandomValuesOnDevice")
         return rs
 
-    def Sample(self, state: State, num_samples: int, seed: int, host_rng: bool = False) -> np.ndarray:
+    def Sample(self, state: State, num_samples: int, seed: int, host_rng: bool = False,
+               norm: Optional[float] = None) -> np.ndarray:
         """lib/statespace_cuda.h:243-312: norm -> sorted random values -> device search.  The values are drawn on
-        the device (the reference's TODO at :292; bit-identical to the host draw, csrc/sample_rng.cu) unless
-        host_rng asks for the reference's host path."""
+        the device (the reference's TODO at :292; bit-identical to the host draw for the same norm,
+        csrc/sample_rng.cu) unless host_rng asks for the reference's host path.  norm: upper bound of the draws;
+        default = Norm(state) on the host path, the total of the sampler's own chunk sums on the device path."""
         out = np.zeros(num_samples, dtype=np.uint64)
         if num_samples > 0:
-            norm = self.Norm(state)
             if host_rng:
+                norm = self.Norm(state) if norm is None else norm
                 rs = self.GenerateRandomValues(num_samples, seed, norm)
                 self.SampleWithValues(state, rs, out)
             else:
+                norm = -1.0 if norm is None else norm
                 self._check(self._lib.qb200_sample_seeded(self._ctx, self._dt, state.get(), state.num_qubits(),
                                                           num_samples, seed, norm,
                                                           out.ctypes.data_as(C.POINTER(C.c_uint64))), "Sample")

@@ -98,8 +98,6 @@ int launch_tcx_shape(qb200_ctx* ctx, float* st, const Geom& g, const float* m, d
   static PerDevice occ_cache;
   const int occ = occ_cache.get(ctx, [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (EXPECT && getenv("QB200_TCX_EXPECT_CARVEOUT"))   // experiment: the carveout the three-tile layout used to get
-      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("QB200_TCX_EXPECT_CARVEOUT")));
     int nb = 512 / tca_tmem_cols<G, 1>();
     const int smem_limit = (int) ((227 * 1024) / (smem + 1024 + 64));
     if (nb > smem_limit) nb = smem_limit;

@@ -38,9 +38,11 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 
 // rs[j] = uniform_real_distribution<double>(0, max_value)(mt19937(seed)), j = 0 .. ns-1, in draw order
 __global__ void __launch_bounds__(kMtThreads)
-k_mt19937_uniform(uint32_t seed, uint64_t ns, double max_value, double* __restrict__ rs) {
+k_mt19937_uniform(uint32_t seed, uint64_t ns, double max_value, const double* __restrict__ d_max_value,
+                  double* __restrict__ rs) {
   __shared__ uint32_t st[2][kMtN];
   const int t = threadIdx.x;
+  if (d_max_value != nullptr) max_value = *d_max_value;   // computed earlier on this stream (the sampler's chunk prefix)
   if (t == 0) {
     uint32_t x = seed;
     st[0][0] = x;
@@ -97,10 +99,11 @@ size_t sorted_uniform_temp_bytes(uint64_t ns) {
 }
 
 // d_sorted[0 .. ns) = the values GenerateRandomValues<double>(ns, seed, max_value) returns, in device memory.
+// d_max_value != nullptr: the upper bound is read from device memory when the kernel runs.
 // d_draws: ns doubles of scratch (draw order); d_temp: sorted_uniform_temp_bytes(ns) bytes.  Enqueued on ctx->stream.
-int sorted_uniform_device(qb200_ctx* ctx, unsigned seed, uint64_t ns, double max_value, double* d_draws,
-                          double* d_sorted, void* d_temp, size_t temp_bytes) {
-  k_mt19937_uniform<<<1, kMtThreads, 0, ctx->stream>>>((uint32_t) seed, ns, max_value, d_draws);
+int sorted_uniform_device(qb200_ctx* ctx, unsigned seed, uint64_t ns, double max_value, const double* d_max_value,
+                          double* d_draws, double* d_sorted, void* d_temp, size_t temp_bytes) {
+  k_mt19937_uniform<<<1, kMtThreads, 0, ctx->stream>>>((uint32_t) seed, ns, max_value, d_max_value, d_draws);
   QB_LAUNCHED(ctx);
   if (cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, (const double*) d_draws, d_sorted, (int64_t) ns, 0, 64,
                                      ctx->stream) != cudaSuccess) {

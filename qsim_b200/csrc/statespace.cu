@@ -200,14 +200,35 @@ __device__ __forceinline__ double slice_sum(const FP* __restrict__ chunk, uint64
   return s;
 }
 
+// out[m] = sum |a|^2 over chunk m.  One block per chunk, 16-byte loads in address order (a warp reads 512 contiguous
+// bytes per instruction): the pass runs at the read roofline.  (Until round 2 thread t summed the contiguous slice
+// [t*per, (t+1)*per) with 8-byte loads 256 bytes apart: 2.5 read-pass equivalents.)  The summation order differs from
+// k_locate's slice-by-slice scan; a draw within round-off of a chunk boundary falls back to the chunk's last index there.
 template <typename FP>
 __global__ void __launch_bounds__(kNT)
 k_chunk_norms(const FP* __restrict__ st, uint64_t chunk_amps, uint64_t nchunks,
               double* __restrict__ out) {
-  const uint64_t per = chunk_amps >= kNT ? chunk_amps / kNT : 1;
+  constexpr int APT = sizeof(FP) == 4 ? 2 : 1;   // amplitudes per 16-byte item
+  const uint64_t items = chunk_amps / APT;
   for (uint64_t m = blockIdx.x; m < nchunks; m += gridDim.x) {
     double s = 0, z = 0;
-    if (threadIdx.x < chunk_amps) s = slice_sum(st + 2 * m * chunk_amps, per, threadIdx.x);
+    if (items >= 1 && (reinterpret_cast<uintptr_t>(st) & 15) == 0) {
+      const uint4* p = reinterpret_cast<const uint4*>(st + 2 * m * chunk_amps);
+      for (uint64_t i = threadIdx.x; i < items; i += kNT) {
+        const uint4 v = __ldg(p + i);
+        if constexpr (APT == 2) {
+          const float a = __uint_as_float(v.x), b = __uint_as_float(v.y), c = __uint_as_float(v.z), d = __uint_as_float(v.w);
+          s += (double) a * a + (double) b * b;
+          s += (double) c * c + (double) d * d;
+        } else {
+          const double a = __hiloint2double(v.y, v.x), b = __hiloint2double(v.w, v.z);
+          s += a * a + b * b;
+        }
+      }
+    } else {
+      const uint64_t per = chunk_amps >= kNT ? chunk_amps / kNT : 1;
+      if (threadIdx.x < chunk_amps) s = slice_sum(st + 2 * m * chunk_amps, per, threadIdx.x);
+    }
     block_sum2<kNT>(s, z);
     if (threadIdx.x == 0) out[m] = s;
   }
@@ -357,8 +378,8 @@ int find_measured_bits(qb200_ctx* ctx, const FP* st, unsigned n, uint64_t m, dou
 
 // sample_rng.cu
 size_t sorted_uniform_temp_bytes(uint64_t ns);
-int sorted_uniform_device(qb200_ctx* ctx, unsigned seed, uint64_t ns, double max_value, double* d_draws,
-                          double* d_sorted, void* d_temp, size_t temp_bytes);
+int sorted_uniform_device(qb200_ctx* ctx, unsigned seed, uint64_t ns, double max_value, const double* d_max_value,
+                          double* d_draws, double* d_sorted, void* d_temp, size_t temp_bytes);
 
 // sorted_rs != nullptr: the caller's sorted values (host memory); else they are drawn on the device from
 // (seed, max_value) exactly as GenerateRandomValues<double> draws them (sample_rng.cu).
@@ -379,18 +400,20 @@ int sample(qb200_ctx* ctx, const FP* st, unsigned n, const double* sorted_rs, un
   double* d_prefix = d_sums + nchunks;
   double* d_rs = d_prefix + nchunks + 1;
   uint64_t* d_out = (uint64_t*) (d_rs + ns);
-  if (sorted_rs) {
-    QB_CUDA(ctx, cudaMemcpyAsync(d_rs, sorted_rs, ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  } else {
-    double* d_draws = (double*) (d_out + ns);
-    void* d_temp = (void*) (((uintptr_t) (d_draws + ns) + 255) & ~uintptr_t{255});
-    rc = sorted_uniform_device(ctx, seed, ns, max_value, d_draws, d_rs, d_temp, temp_bytes);
-    if (rc) return rc;
-  }
   rc = chunk_norms_device(ctx, st, n, d_sums);
   if (rc) return rc;
   k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(d_sums, nchunks, d_prefix);
   QB_LAUNCHED(ctx);
+  if (sorted_rs) {
+    QB_CUDA(ctx, cudaMemcpyAsync(d_rs, sorted_rs, ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    // max_value < 0: draw in [0, total of the chunk sums) -- the state's norm without a separate Norm pass
+    double* d_draws = (double*) (d_out + ns);
+    void* d_temp = (void*) (((uintptr_t) (d_draws + ns) + 255) & ~uintptr_t{255});
+    rc = sorted_uniform_device(ctx, seed, ns, max_value, max_value < 0 ? d_prefix + nchunks : nullptr, d_draws, d_rs,
+                               d_temp, temp_bytes);
+    if (rc) return rc;
+  }
   const uint32_t blocks = (uint32_t) std::min<uint64_t>(ns, 1u << 20);
   k_locate<FP, true><<<blocks, kNT, 0, ctx->stream>>>(st, n, chunk_amps, nchunks, d_prefix, d_rs, ns,
                                                       0, 0.0, d_out);
@@ -553,7 +576,7 @@ int qb200_generate_random_values_device(qb200_ctx* ctx, uint64_t num_samples, un
   double* d_draws = (double*) ctx->scratch;
   double* d_sorted = d_draws + num_samples;
   void* d_temp = (void*) (((uintptr_t) (d_sorted + num_samples) + 255) & ~uintptr_t{255});
-  rc = sorted_uniform_device(ctx, seed, num_samples, max_value, d_draws, d_sorted, d_temp, temp_bytes);
+  rc = sorted_uniform_device(ctx, seed, num_samples, max_value, nullptr, d_draws, d_sorted, d_temp, temp_bytes);
   if (rc) return rc;
   QB_CUDA(ctx, cudaMemcpyAsync(out, d_sorted, num_samples * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   QB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
