@@ -40,5 +40,36 @@ for rdt, cdt in ((np.float32, np.complex64), (np.float64, np.complex128)):
     st3 = ss.Create(3); ss.SetStateUniform(st3)
     mom3 = sim.OneQubitMoments(st3)
     print(rdt.__name__, "batched", len(vals), "moments", mom.shape, float(mom[:, :2].sum(axis=1).max()), mom13.shape, mom3.shape, flush=True)
+    # round 2: device-side random values + seeded sampler, several operators in one pass
+    rs_dev = ss.GenerateRandomValuesOnDevice(1000, 5, 0.9)
+    smp = ss.Sample(st, 700, 3)
+    multi = sim.ExpectationValuesSameQubits([2, 9], [unitary(2, k, cdt) for k in range(5)], st)
+    multi1 = sim.ExpectationValuesSameQubits([0], [unitary(1, k, cdt) for k in range(8)], st)
+    print(rdt.__name__, "device rng", float(rs_dev[0]), int(smp[0]), "multi", multi.shape, multi1.shape, flush=True)
 ss.DeviceSync()
+
+# sharded state on one device (4 shards): both push kernels, the in-place kernel, the copy-engine path and the
+# overlapped pipeline (chunked controlled passes + slim push on a second stream)
+from qsim_b200.sv import ShardedStateB200
+from qsim_b200.trace import TraceOp
+rs = np.random.RandomState(3)
+for rdt, cdt in ((np.float32, np.complex64), (np.float64, np.complex128)):
+    n = 16
+    ops = []
+    for i in range(24):
+        g = int(rs.randint(1, 5))
+        qs = sorted(rs.choice(n, g, replace=False).tolist())
+        ops.append(TraceOp(qs, [], 0, np.ascontiguousarray(unitary(g, i, np.complex64)).reshape(-1).view(np.float32).copy()))
+    for opts in ({"push_kernel": 0}, {"push_kernel": 1}, {"push_kernel": 2}, {"swap_mode": 0},
+                 {"overlap": 1, "overlap_ce": 0}, {"overlap": 1, "overlap_ce": 1, "overlap_chunks_log2": 1}):
+        sv = ShardedStateB200.single_process([0] * 4, n, rdt)
+        for k, v in opts.items():
+            sv.set_option(k, v)
+        sv.SetStateZero()
+        sv.Run(ops)
+        pos = sv.qubit_map()
+        at = {p: q for q, p in enumerate(pos)}
+        sv.Swap([at[12], at[13]], [at[14], at[15]])   # victims at bits 12, 13: the copy-engine path when asked for
+        print(rdt.__name__, opts, "norm", round(sv.Norm(), 6), sv.stats()["swaps"], sv.stats()["copy_engine_swaps"], flush=True)
+        sv.close()
 print("done")
