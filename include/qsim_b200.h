@@ -388,6 +388,12 @@ int qb200_sv_plan(unsigned num_qubits, unsigned num_global, const qb200_gate* ga
 /* explicit exchange of k local (victims) with k global (incoming) logical qubits; restoring pos[q] = q */
 int qb200_sv_swap(qb200_sv* sv, const unsigned* victims, const unsigned* incoming, unsigned k);
 int qb200_sv_canonicalize(qb200_sv* sv);
+/* The initial global set (num_global qubits, ascending) whose schedule for this gate list exchanges the fewest shards
+ * (csrc/sv_plan.h BestInitial): what qb200_sv_run relabels the qubit map to when the state is fresh -- |0...0>, all
+ * zeros or uniform since the last qb200_sv_set_* call, states that look the same under every map, so no data moves
+ * (option "free_initial_map" = 0 keeps the map as it is).  Host-only. */
+int qb200_sv_plan_initial(unsigned num_qubits, unsigned num_global, const qb200_gate* gates, uint64_t count, int reorder,
+                          unsigned* global_qubits_out);
 
 #ifdef __cplusplus
 }

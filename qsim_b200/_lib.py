@@ -144,6 +144,7 @@ SIGNATURES.update({
     "qb200_sv_expectation_value": (_i, [_vp, _pu, _u, _vp, _pd]),
     "qb200_sv_run": (_i, [_vp, C.POINTER(Gate), _u64]),
     "qb200_sv_plan": (_i, [_u, _u, C.POINTER(Gate), _u64, _pu, _i, C.POINTER(C.c_int64), _u64, _pu64]),
+    "qb200_sv_plan_initial": (_i, [_u, _u, _vp, _u64, _i, _pu]),
     "qb200_sv_swap": (_i, [_vp, _pu, _pu, _u]),
     "qb200_sv_canonicalize": (_i, [_vp]),
 })

@@ -390,6 +390,11 @@ struct qb200_sv {
   int overlap_ctas_per_sm = 0;           // CTAs per SM of the slim push kernel that runs beside gates (0 = 1)
   int overlap_smem_kb = 0;               // ... and its shared memory per CTA (0 = 16 KB)
   int overlap_tile_bits = 9;             // ... which moves tiles of 2^this amplitudes (4 KB in fp32)
+  bool fresh = false;                    // the state is |0...0> / all zeros / uniform and nothing has touched it since: it looks
+                                         // the same under every qubit map, so qb200_sv_run may pick the map for the circuit
+  int free_initial_map = 1;              // ... and does, unless this is 0
+  std::vector<uint64_t> init_key;        // gate structure the cached initial global set was chosen for
+  uint64_t init_glob = 0;
   int overlap = 0;                       // qb200_sv_run: the last gates of an epoch run beside its exchange, chunk by chunk
                                          // (off by default: measured no gain on B200, profiles/r02_overlap_trace.txt)
   int overlap_chunks_log2 = 2;           // 2^this chunks per shard
@@ -634,6 +639,7 @@ static int local_gate(qb200_sv* sv, const unsigned* qs, unsigned nq, const unsig
                       const unsigned* chunk_bits = nullptr, unsigned nchunk = 0, unsigned chunk_val = 0) {
   if (nq > kMaxTargets) return QB200_ERR_UNSUPPORTED;
   if (nc > 0 && nq > kMaxCtrlTargets) return QB200_ERR_UNSUPPORTED;
+  if (!expect) sv->fresh = false;
   unsigned phys[kMaxTargets], order[kMaxTargets], sorted[kMaxTargets];
   for (unsigned j = 0; j < nq; ++j) {
     if (qs[j] >= sv->n) return QB200_ERR_INVALID;
@@ -1035,6 +1041,7 @@ static int order_pairs(qb200_sv* sv, const unsigned* victims_in, const unsigned*
 // victims (logical, local) <-> incoming (logical, global); k <= g.
 static int exchange(qb200_sv* sv, const unsigned* victims_in, const unsigned* incoming_in, unsigned k) {
   if (k == 0) return QB200_OK;
+  sv->fresh = false;
   std::vector<unsigned> victims, incoming;
   SV_TRY(order_pairs(sv, victims_in, incoming_in, k, &victims, &incoming));
   unsigned gb[kMaxGlobal];
@@ -1457,6 +1464,7 @@ int qb200_sv_set_option(qb200_sv* sv, const char* key, int value) {
   else if (!std::strcmp(key, "overlap_max_gates")) sv->overlap_max_gates = value;
   else if (!std::strcmp(key, "overlap_occ_reduce")) sv->overlap_occ_reduce = value;
   else if (!std::strcmp(key, "overlap_trace")) sv->overlap_trace = value;
+  else if (!std::strcmp(key, "free_initial_map")) sv->free_initial_map = value;
   else if (!std::strcmp(key, "overlap_ce")) sv->overlap_ce = value;
   else if (!std::strcmp(key, "overlap_ctas_per_sm")) sv->overlap_ctas_per_sm = value;
   else if (!std::strcmp(key, "overlap_smem_kb")) sv->overlap_smem_kb = value;
@@ -1506,6 +1514,7 @@ int qb200_sv_reset_stats(qb200_sv* sv) {
 int qb200_sv_set_all_zeros(qb200_sv* sv) {
   if (!sv) return QB200_ERR_INVALID;
   for (auto& s : sv->sh) SV_TRY(qb200_set_all_zeros(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl));
+  sv->fresh = true;
   return QB200_OK;
 }
 
@@ -1514,6 +1523,7 @@ int qb200_sv_set_state_zero(qb200_sv* sv) {
   SV_TRY(qb200_sv_set_all_zeros(sv));
   // |0...0> is index 0 under every qubit map
   if (Shard* s = local_shard(sv, 0)) SV_TRY(qb200_set_ampl(s->ctx, sv->dtype, cur_buf(sv, *s), 0, 1.0, 0.0));
+  sv->fresh = true;
   return QB200_OK;
 }
 
@@ -1521,6 +1531,7 @@ int qb200_sv_set_state_uniform(qb200_sv* sv) {
   if (!sv) return QB200_ERR_INVALID;
   const double v = 1.0 / std::sqrt((double) (uint64_t{1} << sv->n));  // lib/statespace_cuda.h:122
   for (auto& s : sv->sh) SV_TRY(qb200_bulk_set_ampl(s.ctx, sv->dtype, cur_buf(sv, s), sv->nl, 0, 0, v, 0.0, 0));
+  sv->fresh = true;
   return QB200_OK;
 }
 
@@ -1557,6 +1568,7 @@ int qb200_sv_get_ampls(qb200_sv* sv, const uint64_t* indices, uint64_t count, do
 
 int qb200_sv_set_ampl(qb200_sv* sv, uint64_t i, double re, double im) {
   if (!sv || (i >> sv->n)) return QB200_ERR_INVALID;
+  sv->fresh = false;
   const uint64_t p = to_physical(sv, i);
   if (Shard* s = local_shard(sv, (unsigned) (p >> sv->nl)))
     SV_TRY(qb200_set_ampl(s->ctx, sv->dtype, cur_buf(sv, *s), p & ((uint64_t{1} << sv->nl) - 1), re, im));
@@ -1565,6 +1577,7 @@ int qb200_sv_set_ampl(qb200_sv* sv, uint64_t i, double re, double im) {
 
 int qb200_sv_bulk_set_ampl(qb200_sv* sv, uint64_t mask, uint64_t bits, double re, double im, int exclude) {
   if (!sv) return QB200_ERR_INVALID;
+  sv->fresh = false;
   const uint64_t pm = to_physical(sv, mask), pb = to_physical(sv, bits);
   const uint64_t lmask = pm & ((uint64_t{1} << sv->nl) - 1), lbits = pb & ((uint64_t{1} << sv->nl) - 1);
   const uint64_t gmask = pm >> sv->nl, gbits = pb >> sv->nl;
@@ -1611,25 +1624,15 @@ int qb200_sv_swap(qb200_sv* sv, const unsigned* victims, const unsigned* incomin
 
 int qb200_sv_canonicalize(qb200_sv* sv) { return sv ? canonicalize(sv) : QB200_ERR_INVALID; }
 
+static int gate_masks(unsigned num_qubits, unsigned num_global, const qb200_gate* gates, uint64_t count,
+                      std::vector<uint64_t>* touch_m, std::vector<uint64_t>* need);
+
 int qb200_sv_plan(unsigned num_qubits, unsigned num_global, const qb200_gate* gates, uint64_t count,
                   const unsigned* global_qubits, int reorder, int64_t* steps, uint64_t capacity, uint64_t* num_steps) {
   if (!gates && count) return QB200_ERR_INVALID;
   if (num_qubits > 63 || num_global > num_qubits) return QB200_ERR_INVALID;
-  std::vector<uint64_t> touch_m(count), need(count);
-  for (uint64_t i = 0; i < count; ++i) {
-    uint64_t t = 0, c = 0;
-    for (unsigned j = 0; j < gates[i].num_targets; ++j) {
-      if (gates[i].qs[j] >= num_qubits) return QB200_ERR_INVALID;
-      t |= uint64_t{1} << gates[i].qs[j];
-    }
-    for (unsigned j = 0; j < gates[i].num_controls; ++j) {
-      if (gates[i].cqs[j] >= num_qubits) return QB200_ERR_INVALID;
-      c |= uint64_t{1} << gates[i].cqs[j];
-    }
-    if ((unsigned) __builtin_popcountll(t) > num_qubits - num_global) return QB200_ERR_UNSUPPORTED;
-    touch_m[i] = t | c;
-    need[i] = t;
-  }
+  std::vector<uint64_t> touch_m, need;
+  SV_TRY(gate_masks(num_qubits, num_global, gates, count, &touch_m, &need));
   uint64_t glob = 0;
   for (unsigned j = 0; j < num_global; ++j)
     glob |= uint64_t{1} << (global_qubits ? global_qubits[j] : num_qubits - num_global + j);
@@ -1652,6 +1655,63 @@ int qb200_sv_plan(unsigned num_qubits, unsigned num_global, const qb200_gate* ga
   return (steps && w > capacity) ? QB200_ERR_INVALID : QB200_OK;
 }
 
+// touch / need masks of a gate list (qb200_sv_plan's input); QB200_ERR_INVALID for a qubit out of range
+static int gate_masks(unsigned num_qubits, unsigned num_global, const qb200_gate* gates, uint64_t count,
+                      std::vector<uint64_t>* touch_m, std::vector<uint64_t>* need) {
+  touch_m->assign(count, 0);
+  need->assign(count, 0);
+  for (uint64_t i = 0; i < count; ++i) {
+    uint64_t t = 0, c = 0;
+    for (unsigned j = 0; j < gates[i].num_targets; ++j) {
+      if (gates[i].qs[j] >= num_qubits) return QB200_ERR_INVALID;
+      t |= uint64_t{1} << gates[i].qs[j];
+    }
+    for (unsigned j = 0; j < gates[i].num_controls; ++j) {
+      if (gates[i].cqs[j] >= num_qubits) return QB200_ERR_INVALID;
+      c |= uint64_t{1} << gates[i].cqs[j];
+    }
+    if ((unsigned) __builtin_popcountll(t) > num_qubits - num_global) return QB200_ERR_UNSUPPORTED;
+    (*touch_m)[i] = t | c;
+    (*need)[i] = t;
+  }
+  return QB200_OK;
+}
+
+int qb200_sv_plan_initial(unsigned num_qubits, unsigned num_global, const qb200_gate* gates, uint64_t count, int reorder,
+                          unsigned* global_qubits_out) {
+  if ((!gates && count) || !global_qubits_out || num_qubits > 63 || num_global > num_qubits) return QB200_ERR_INVALID;
+  std::vector<uint64_t> touch_m, need;
+  SV_TRY(gate_masks(num_qubits, num_global, gates, count, &touch_m, &need));
+  uint64_t def = 0;
+  for (unsigned j = 0; j < num_global; ++j) def |= uint64_t{1} << (num_qubits - num_global + j);
+  const uint64_t best = SwapPlanner::BestInitial(num_qubits, num_global, touch_m, need, def, reorder != 0);
+  unsigned w = 0;
+  for (unsigned q = 0; q < num_qubits; ++q)
+    if ((best >> q) & 1) global_qubits_out[w++] = q;
+  return QB200_OK;
+}
+
+// The state is fresh (|0...0>, zeros or uniform: the same under every qubit map): relabel the map so that the global
+// qubits are the set whose schedule for THIS circuit exchanges the fewest shards.  No data moves.
+static int choose_initial_map(qb200_sv* sv, const qb200_gate* gates, uint64_t count) {
+  if (sv->g == 0) return QB200_OK;
+  std::vector<uint64_t> touch_m, need;
+  SV_TRY(gate_masks(sv->n, sv->g, gates, count, &touch_m, &need));
+  std::vector<uint64_t> key;
+  key.reserve(2 * count + 1);
+  key.push_back((uint64_t) sv->reorder);
+  for (uint64_t i = 0; i < count; ++i) { key.push_back(touch_m[i]); key.push_back(need[i]); }
+  if (key != sv->init_key) {
+    uint64_t cur = 0;
+    for (unsigned t = 0; t < sv->g; ++t) cur |= uint64_t{1} << qubit_at(sv, sv->nl + t);
+    sv->init_glob = SwapPlanner::BestInitial(sv->n, sv->g, touch_m, need, cur, sv->reorder != 0);
+    sv->init_key = key;
+  }
+  unsigned il = 0, ig = 0;
+  for (unsigned q = 0; q < sv->n; ++q) sv->pos[q] = ((sv->init_glob >> q) & 1) ? sv->nl + ig++ : il++;
+  return QB200_OK;
+}
+
 int qb200_sv_run(qb200_sv* sv, const qb200_gate* gates, uint64_t count) {
   if (!sv || (!gates && count)) return QB200_ERR_INVALID;
   for (uint64_t i = 0; i < count; ++i) {
@@ -1665,6 +1725,7 @@ int qb200_sv_run(qb200_sv* sv, const qb200_gate* gates, uint64_t count) {
                         gates[i].matrix, false, nullptr));
     return QB200_OK;
   }
+  if (sv->fresh && sv->free_initial_map && count > 0) SV_TRY(choose_initial_map(sv, gates, count));
   std::vector<unsigned> glob;
   for (unsigned t = 0; t < sv->g; ++t) glob.push_back(qubit_at(sv, sv->nl + t));
   // the schedule depends only on which qubits each gate touches and on the current global set: a circuit that
@@ -1800,6 +1861,7 @@ int qb200_sv_inner_product(qb200_sv* a, qb200_sv* b, double out[2]) {
 
 int qb200_sv_add(qb200_sv* src, qb200_sv* dest) {
   if (!same_shape(src, dest)) return QB200_ERR_INVALID;
+  dest->fresh = false;
   SV_TRY(align_maps(src, dest));
   for (size_t i = 0; i < src->sh.size(); ++i) {
     DevScope d(dest->sh[i].device);
@@ -1828,11 +1890,13 @@ int qb200_sv_copy(qb200_sv* src, qb200_sv* dest) {
     cudaStreamWaitEvent(src->sh[i].stream, dest->sh[i].ev, 0);
   }
   dest->pos = src->pos;
+  dest->fresh = src->fresh;
   return sync_all(dest);
 }
 
 int qb200_sv_multiply(qb200_sv* sv, double a) {
   if (!sv) return QB200_ERR_INVALID;
+  sv->fresh = false;
   for (auto& s : sv->sh) SV_TRY(qb200_multiply(s.ctx, sv->dtype, a, cur_buf(sv, s), sv->nl));
   return QB200_OK;
 }
@@ -1902,6 +1966,7 @@ int qb200_sv_find_measured_bits(qb200_sv* sv, uint64_t m, double r, uint64_t mas
 
 int qb200_sv_collapse(qb200_sv* sv, uint64_t mask, uint64_t bits, double* out_norm) {
   if (!sv) return QB200_ERR_INVALID;
+  sv->fresh = false;
   const uint64_t pm = to_physical(sv, mask), pb = to_physical(sv, bits);
   const uint64_t lmask = pm & ((uint64_t{1} << sv->nl) - 1), lbits = pb & ((uint64_t{1} << sv->nl) - 1);
   const uint64_t gmask = pm >> sv->nl, gbits = pb >> sv->nl;
@@ -1932,6 +1997,7 @@ int qb200_sv_copy_to_host(qb200_sv* sv, void* host) {
 
 int qb200_sv_copy_from_host(qb200_sv* sv, const void* host) {
   if (!sv || !host) return QB200_ERR_INVALID;
+  sv->fresh = false;
   for (unsigned q = 0; q < sv->n; ++q) sv->pos[q] = q;
   const size_t bytes = shard_bytes(sv);
   for (auto& s : sv->sh) {

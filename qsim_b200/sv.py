@@ -65,6 +65,17 @@ def plan(num_qubits: int, num_global: int, ops, global_qubits: Optional[Sequence
     return out
 
 
+def plan_initial(num_qubits: int, num_global: int, ops, reorder: bool = True):
+    """The initial global qubits qb200_sv_run picks for this circuit on a fresh state (qb200_sv_plan_initial)."""
+    lib = _lib.load()
+    arr, keep = pack_gates(ops)
+    out = (C.c_uint * max(num_global, 1))()
+    rc = lib.qb200_sv_plan_initial(num_qubits, num_global, arr, len(ops), int(reorder), out)
+    if rc != OK:
+        raise QB200Error(rc, "qb200_sv_plan_initial")
+    return [int(out[j]) for j in range(num_global)]
+
+
 class _TorchComm:
     """qb200_comm over torch.distributed (host buffers; staged through a tensor on `device` for NCCL)."""
 

@@ -345,6 +345,31 @@ def test_library_planner_on_the_benchmark_circuits():
     assert all(s[0] == "gate" for s in sched)
 
 
+def test_initial_global_set_is_chosen_for_the_circuit():
+    """qb200_sv_plan_initial (csrc/sv_plan.h BestInitial): on a fresh state the qubit map is free, so the library picks
+    the initial global qubits whose schedule exchanges the fewest shards -- never worse than the default (top g qubits),
+    which it keeps on ties."""
+    from qsim_b200 import sv
+    from qsim_b200.trace import TraceOp
+    x = np.array([0, 0, 1, 0, 1, 0, 0, 0], np.float32)
+
+    def cost(steps):
+        return sum(1 - 0.5 ** len(s[1]) for s in steps if s[0] == "swap")
+
+    # every gate sits on the top qubits, qubits 0 and 1 are never touched: with them global no exchange is needed
+    ops = [TraceOp([q], [], 0, x) for q in (7, 6, 5, 7, 4, 6, 3, 2)]
+    for g in (1, 2):
+        init = sv.plan_initial(8, g, ops)
+        assert set(init) <= {0, 1} and len(init) == g
+        assert cost(sv.plan(8, g, ops, global_qubits=init)) == 0 < cost(sv.plan(8, g, ops))
+    # the benchmark circuits: the default set is already optimal within the search, and is kept
+    for n, g in ((31, 1), (32, 2), (33, 3)):
+        _, rops = read_trace(os.path.join(ROOT, "tests", "golden", f"rqc_q{n}_d20_f4.trace"))
+        init = sv.plan_initial(n, g, rops)
+        assert cost(sv.plan(n, g, rops, global_qubits=init)) <= cost(sv.plan(n, g, rops)) + 1e-12
+        assert init == list(range(n - g, n))
+
+
 def test_sharded_rqc_trace_world2(tmp_path):
     n, ops = read_trace(os.path.join(ROOT, "tests", "golden", "rqc_q20_d20_f4.trace"))
     ops = ops[:14]

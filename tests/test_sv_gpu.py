@@ -210,6 +210,42 @@ def test_exchange_overlapped_with_the_last_gates_of_the_epoch(oracle, shards, ch
     assert np.abs(states[0] - states[1]).max() < tol
 
 
+def test_fresh_state_gets_the_qubit_map_the_circuit_wants(oracle):
+    """|0...0> looks the same under every qubit map: qb200_sv_run relabels the map of a fresh state so that the
+    circuit's best initial global qubits are global (no data moves).  Gates only on the top qubits: the default map
+    needs exchanges, the chosen one none; the state is the oracle's either way, and a state that is no longer fresh
+    keeps its map."""
+    from qsim_b200.trace import TraceOp
+    n, shards = 14, 4
+    rs = np.random.RandomState(4)
+    ops = []
+    for i in range(12):
+        qs = sorted(rs.choice(np.arange(4, n), 2, replace=False).tolist())   # qubits 0..3 are never touched
+        ops.append(TraceOp(qs, [], 0, np.ascontiguousarray(random_unitary(2, i, np.complex64)).reshape(-1).view(np.float32).copy()))
+    want = oracle_run(oracle, n, ops)
+    st = make(shards, n)
+    st.SetStateZero()
+    st.Run(ops)
+    assert st.stats()["swaps"] == 0 and sorted(q for q, p in enumerate(st.qubit_map()) if p >= n - 2) in ([0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3])
+    assert np.abs(st.to_numpy() - want).max() < 3e-6
+    pinned = make(shards, n, free_initial_map=0)
+    pinned.SetStateZero()
+    pinned.Run(ops)
+    assert pinned.stats()["swaps"] >= 1
+    assert np.abs(pinned.to_numpy() - want).max() < 3e-6
+    # a state that has been touched is not fresh: its map stays, the same circuit needs its exchanges
+    touched = make(shards, n)
+    touched.SetStateZero()
+    h = random_unitary(1, 99, np.complex64)
+    touched.ApplyGate([5], h)
+    touched.Run(ops)
+    assert touched.stats()["swaps"] >= 1
+    first = TraceOp([5], [], 0, np.ascontiguousarray(h).reshape(-1).view(np.float32).copy())
+    assert np.abs(touched.to_numpy() - oracle_run(oracle, n, [first] + ops)).max() < 3e-6
+    touched.close()
+    st.close(); pinned.close()
+
+
 @pytest.mark.parametrize("push_kernel", [0, 1])
 def test_run_fp64(oracle, push_kernel):
     n, shards = 13, 4
