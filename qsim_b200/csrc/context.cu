@@ -206,7 +206,7 @@ using namespace qb200;
 
 extern "C" {
 
-int qb200_abi_version(void) { return 2; }
+int qb200_abi_version(void) { return 3; }   // 3: qb200_sv_stats grew (overlap / copy-engine counters), seeded sampler, operator groups
 
 uint64_t qb200_mutation_epoch(void) { return g_mutation_epoch.load(std::memory_order_relaxed); }
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for s in declared_symbols():
         assert hasattr(lib, s), s
-    assert lib.qb200_abi_version() == 2
+    assert lib.qb200_abi_version() == 3
 
 
 def test_host_only_entry_points():
