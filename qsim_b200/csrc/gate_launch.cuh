@@ -320,19 +320,33 @@ int gate_pass(qb200_ctx* ctx, FP* st, unsigned n, const unsigned* qs, unsigned n
     }
   }
 
-  // fp64 G = 5, 6 gates and G = 4, 5, 6 expectation values: row-blocked DFMA kernel (gate_dbig.cuh)
+  // fp64 G = 4, 5, 6 gates and expectation values: register-blocked complex GEMM (gate_dbig.cuh k_gate_d6) once the
+  // pass has whole tiles of 2^(12 - G) groups.  Tuning big: 1 = the round-1 selection (G = 4, 5 gates and G = 4
+  // expectation values on the unrolled register kernels with constant-bank matrix operands, G = 5 expectation values
+  // on k_gate_dbig, G = 6 on k_gate_d6); 2 = k_gate_dbig for G = 5 gates and G = 4 expectation values too; 3 = like 1
+  // with k_gate_dbig for G = 6 (the cross-check in the tests); 0 = none of these kernels.
   if constexpr (sizeof(FP) == 8) {
-    // G = 6 always; G = 4, 5 only with tuning big = 2 (default: fully unrolled register kernels whose matrix
-    // elements are constant-bank operands of the DFMAs -- no load per MAC)
-    const bool want = nq == 6 || (EXPECT && nq == 5) || (ctx->tune.big == 2 && (EXPECT ? nq >= 4 : nq == 5));
-    if (!ctx->tune.force_generic && want && nq <= 6 && ctx->tune.big != 0) {
+    if (!ctx->tune.force_generic && nq >= 4 && nq <= 6 && ctx->tune.big != 0) {
       Geom dg;
       int drc = make_geom(n, qs, nq, cqs, nc, cvals, false, &dg);
       if (drc) return drc;
-      ctx->last_kernel = "k_gate_dbig";
-      if (nq == 4) { if constexpr (EXPECT) return launch_dbig<4, true>(ctx, st, dg, m, out); }
-      if (nq == 5) return launch_dbig<5, EXPECT>(ctx, st, dg, m, out);
-      if (nq == 6) return launch_dbig<6, EXPECT>(ctx, st, dg, m, out);
+      const int big = ctx->tune.big;
+      const bool gemm = big == -1 || (nq == 6 && big != 3);
+      if (gemm) {
+        ctx->last_kernel = "k_gate_d6";
+        // (G = 4 with bit 0 among the targets: group elements 16 bytes apart, the per-group loads do not coalesce --
+        //  5.9-7.6 ms against 5.0-5.6 on the register kernels)
+        if (nq == 4 && d6_fits<4>(dg) && qs[0] >= 1) return launch_d6<4, EXPECT>(ctx, st, dg, m, out);
+        if (nq == 5 && d6_fits<5>(dg)) return launch_d6<5, EXPECT>(ctx, st, dg, m, out);
+        if (nq == 6 && d6_fits<6>(dg)) return launch_d6<6, EXPECT>(ctx, st, dg, m, out);
+      }
+      const bool want = nq == 6 || (EXPECT && nq == 5) || (big == 2 && (EXPECT ? nq >= 4 : nq == 5));
+      if (want) {
+        ctx->last_kernel = "k_gate_dbig";
+        if (nq == 4) { if constexpr (EXPECT) return launch_dbig<4, true>(ctx, st, dg, m, out); }
+        if (nq == 5) return launch_dbig<5, EXPECT>(ctx, st, dg, m, out);
+        if (nq == 6) return launch_dbig<6, EXPECT>(ctx, st, dg, m, out);
+      }
     }
   }
 

@@ -562,3 +562,46 @@ def test_expectation_values_of_several_operators_in_one_pass(oracle, cdt):
     assert e.value.status == _lib.ERR_UNSUPPORTED
     with pytest.raises(qsim_b200.QB200Error):
         sim.ExpectationValuesSameQubits([0], [np.eye(2)] * 9, st)
+
+
+@pytest.mark.parametrize("g", [4, 5, 6])
+def test_fp64_register_blocked_gemm_kernel(oracle, g):
+    """k_gate_d6 (csrc/gate_dbig.cuh): fp64 gates and expectation values on 4, 5, 6 qubits as a register-blocked
+    complex GEMM over tiles of 2^(12 - G) groups -- every class of layout (low / high / mixed targets, target 0
+    in and out), a controlled 4-qubit gate, against the oracle in double; the round-1 kernels (tuning big = 3) agree."""
+    import qsim_b200
+    ss, sim = qsim_b200.StateSpaceB200(np.float64), qsim_b200.SimulatorB200(np.float64)
+    n = 15
+    h = random_state(n, np.complex128, 40 + g)
+    rng = np.random.default_rng(g)
+    layouts = [list(range(g)), list(range(n - g, n)), list(range(3, 3 + g)), [0] + list(range(n - g + 1, n)),
+               [1] + list(range(6, 5 + g))] + [sorted(rng.choice(n, g, replace=False).tolist()) for _ in range(4)]
+    for qs in layouts:
+        u = random_unitary(g, 7 * g + qs[0], np.complex128)
+        st = ss.Create(n)
+        ss.from_numpy(h, st)
+        gemm = not (g == 4 and qs[0] == 0)   # 4 targets with bit 0 among them stay on the register kernels
+        ev = sim.ExpectationValue(qs, u, st)
+        assert (sim.last_kernel_name() == "k_gate_d6") == gemm
+        assert abs(ev - oracle.expectation_value(h, qs, u)) < 1e-12
+        assert np.array_equal(ss.to_numpy(st), h)
+        sim.ApplyGate(qs, u, st)
+        assert (sim.last_kernel_name() == "k_gate_d6") == gemm
+        want = h.copy()
+        oracle.apply_gate(want, qs, u)
+        got = ss.to_numpy(st)
+        assert np.abs(got - want).max() < 1e-14, qs
+        sim.set_tuning("big", 3)
+        ss.from_numpy(h, st)
+        sim.ApplyGate(qs, u, st)
+        assert sim.last_kernel_name() != "k_gate_d6"
+        assert np.abs(ss.to_numpy(st) - got).max() < 1e-14
+        sim.set_tuning("big", -1)
+    if g == 4:
+        u = random_unitary(4, 3, np.complex128)
+        st = ss.Create(n)
+        ss.from_numpy(h, st)
+        sim.ApplyControlledGate([2, 5, 9, 12], [0, 14], 0b10, u, st)
+        want = h.copy()
+        oracle.apply_controlled_gate(want, [2, 5, 9, 12], [0, 14], 0b10, u)
+        assert np.abs(ss.to_numpy(st) - want).max() < 1e-14
