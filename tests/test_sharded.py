@@ -423,3 +423,125 @@ def test_reindex_matrix():
     # float (interleaved) input gives the same answer
     bits_f, m2f = reindex_matrix(m.reshape(-1).view(np.float32).copy(), [4, 1, 3])
     assert np.array_equal(m2f.view(np.complex64).reshape(8, 8), m2)
+
+
+# ---- index arithmetic of the chunked exchange (csrc/sharded.cu), restated in numpy ----------------------------------
+def _new_layout_reference(nl, lbits, my):
+    """where amplitude i of a shard goes: (destination value of the victim bits, index in the destination buffer) --
+    the definition (victim bits squeezed out, order of the rest kept, this shard's rank-bit value on top)"""
+    k = len(lbits)
+    i = np.arange(1 << nl, dtype=np.int64)
+    v = np.zeros_like(i)
+    packed = np.zeros_like(i)
+    w = 0
+    for b in range(nl):
+        if b in lbits:
+            v |= ((i >> b) & 1) << lbits.index(b)
+        else:
+            packed |= ((i >> b) & 1) << w
+            w += 1
+    return v, (my << (nl - k)) | packed
+
+
+def _push_kernel_walk(nl, T, lbits, my, chunk_bits):
+    """k_remap_push / k_remap_push_tma: every chunk's tile counters -> (source tile, destination, offset), with the
+    chunk bits pinned through chunk_counter (run_overlapped computes cpos the same way)."""
+    k = len(lbits)
+    kl = sum(1 for b in lbits if b < T)
+    kh = k - kl
+    sub_bits = T - kl
+    my_high = my >> kl
+    tiles = 1 << (nl - T)
+    c = len(chunk_bits)
+    cpos = [kh + (cb - T) - sum(1 for b in lbits[kl:] if b < cb) for cb in chunk_bits]
+    dst_v = np.full(1 << nl, -1, np.int64)
+    dst_i = np.full(1 << nl, -1, np.int64)
+    for cval in range(1 << c):
+        for cc in range(tiles >> c):
+            cnt = cc
+            for j in range(c):   # chunk_counter
+                lo = cnt & ((1 << cpos[j]) - 1)
+                cnt = (((cnt >> cpos[j]) << 1 | ((cval >> j) & 1)) << cpos[j]) | lo
+            v_high = (cnt & ((1 << kh) - 1)) ^ my_high
+            tau = cnt >> kh
+            for j in range(kl, k):
+                b = lbits[j] - T
+                lo = tau & ((1 << b) - 1)
+                tau = (((tau >> b) << 1 | ((v_high >> (j - kl)) & 1)) << b) | lo
+            packed_high = cnt >> kh
+            for a in range(1 << T):   # amplitude a of the tile: sorted by its low victim bits
+                v, r = 0, a
+                for j in range(kl - 1, -1, -1):
+                    b = lbits[j]
+                    v |= ((r >> b) & 1) << j
+                    r = ((r >> (b + 1)) << b) | (r & ((1 << b) - 1))
+                src = (tau << T) | a
+                assert dst_v[src] == -1
+                dst_v[src] = v | (v_high << kl)
+                dst_i[src] = (my << (nl - k)) | (packed_high << sub_bits) | r
+                # the chunk bits of the source index carry cval
+                for j, cb in enumerate(chunk_bits):
+                    assert (src >> cb) & 1 == (cval >> j) & 1
+    return dst_v, dst_i
+
+
+def _copy_engine_boxes(nl, lbits, my, chunk_bits):
+    """ce_push: free-bit runs between the pinned bits; the longest run above the row is the height of a 2-D copy, the
+    others are looped over; the destination has the same runs at the packed positions."""
+    k = len(lbits)
+    dpos = lambda bit: bit - sum(1 for b in lbits if b < bit)
+    dst_v = np.full(1 << nl, -1, np.int64)
+    dst_i = np.full(1 << nl, -1, np.int64)
+    sp = sorted(lbits + chunk_bits)
+    runs, lo = [], 0
+    for b in sp:
+        if b > lo:
+            runs.append((lo, b - lo))
+        lo = b + 1
+    if nl > lo:
+        runs.append((lo, nl - lo))
+    assert runs and runs[0][0] == 0
+    boxed = max(range(1, len(runs)), key=lambda r: (runs[r][1], -r)) if len(runs) > 1 else None
+    loops = [runs[r] for r in range(1, len(runs)) if r != boxed]
+    width = 1 << runs[0][1]
+    for cval in range(1 << len(chunk_bits)):
+        src_fixed = sum(((cval >> j) & 1) << cb for j, cb in enumerate(chunk_bits))
+        dst_fixed = (my << (nl - k)) | sum(((cval >> j) & 1) << dpos(cb) for j, cb in enumerate(chunk_bits))
+        for v in range(1 << k):
+            src_v = src_fixed | sum(((v >> j) & 1) << lbits[j] for j in range(k))
+            nloop = 1 << sum(ln for _, ln in loops)
+            for it in range(nloop):
+                so, do, rest = src_v, dst_fixed, it
+                for start, ln in loops:
+                    val = rest & ((1 << ln) - 1)
+                    rest >>= ln
+                    so |= val << start
+                    do |= val << dpos(start)
+                height = 1 << runs[boxed][1] if boxed is not None else 1
+                spitch = 1 << runs[boxed][0] if boxed is not None else 0
+                dpitch = 1 << dpos(runs[boxed][0]) if boxed is not None else 0
+                for h in range(height):
+                    s0, d0 = so + h * spitch, do + h * dpitch
+                    assert np.all(dst_v[s0:s0 + width] == -1)
+                    dst_v[s0:s0 + width] = v
+                    dst_i[s0:s0 + width] = np.arange(d0, d0 + width)
+    return dst_v, dst_i
+
+
+def test_chunked_exchange_index_arithmetic():
+    """Both ways of moving a shard chunk by chunk -- the push kernels' tile walk with pinned counter bits and the copy
+    engines' pitched boxes -- cover every amplitude exactly once and put it where the definition of the new layout
+    says, for victims inside / above the tile, adjacent or apart, 0-3 chunk bits."""
+    nl, T = 16, 6
+    cases = [([15], [13, 14]), ([2], [14, 15]), ([3, 9], [12, 15]), ([7, 8, 12], [10, 14, 15]), ([0, 1], []),
+             ([13, 14, 15], [11, 12]), ([5], [15])]
+    for lbits, chunk_bits in cases:
+        for my in (0, (1 << len(lbits)) - 1):
+            want_v, want_i = _new_layout_reference(nl, lbits, my)
+            got_v, got_i = _push_kernel_walk(nl, T, lbits, my, chunk_bits)
+            assert np.array_equal(got_v, want_v) and np.array_equal(got_i, want_i), (lbits, chunk_bits)
+    for lbits, chunk_bits in [([12], [14, 15]), ([12, 13], [15]), ([13, 15], [12, 14]), ([14], []), ([12, 14, 15], [13])]:
+        for my in (0, (1 << len(lbits)) - 1):
+            want_v, want_i = _new_layout_reference(nl, lbits, my)
+            got_v, got_i = _copy_engine_boxes(nl, lbits, my, chunk_bits)
+            assert np.array_equal(got_v, want_v) and np.array_equal(got_i, want_i), (lbits, chunk_bits)
